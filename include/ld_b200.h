@@ -1,0 +1,145 @@
+/* ld_b200.h -- C ABI of the B200-native laughter-detection hot path.
+ *
+ * The reference (LasseWolter/laughter-detection-icsi) is pure Python and has no FFI of its own; the
+ * drop-in boundary is its Python surface.  Each entry point below names the
+ * reference call it replaces (file:line in the reference tree).  The Python host mirror in
+ * laughter_detection_icsi_b200/ binds these symbols with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions: plain C types only; every `*_d` / "device" pointer is a CUDA device pointer owned by the
+ * caller, every "host" pointer is ordinary host memory; `stream` is a cudaStream_t passed as void*
+ * (NULL = legacy default stream); functions return 0 on success or a negative ld_status and record a
+ * message retrievable with ld_last_error() (thread local).  One ld_ctx per GPU per process; a context
+ * is not thread-safe, distinct contexts are independent.  No entry point ever falls back to the CPU.
+ */
+#ifndef LD_B200_H_
+#define LD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define LD_API __attribute__((visibility("default")))
+#else
+#define LD_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ld_ctx ld_ctx;
+
+enum ld_status {
+    LD_OK = 0,
+    LD_ERR_INVALID = -1,   /* bad argument */
+    LD_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+    LD_ERR_STATE = -3,     /* e.g. weights not loaded */
+    LD_ERR_CAPACITY = -4,  /* output buffer too small */
+    LD_ERR_UNSUPPORTED = -5
+};
+
+/* Feature front-end variant (ambiguity ii). */
+enum ld_fbank_preproc {
+    LD_PREPROC_UTTERANCE = 0, /* Lhotse Wav2Win: DC removal + pre-emphasis over the whole recording */
+    LD_PREPROC_FRAME = 1      /* Kaldi / torchaudio.compliance.kaldi: per 400-sample frame */
+};
+
+typedef struct ld_config {
+    int32_t struct_size;     /* sizeof(ld_config), for forward compatibility */
+    int32_t num_frames;      /* window length in frames, config.FEAT['num_samples'] (config.py:29) = 100 */
+    int32_t num_filters;     /* mel bins, config.FEAT['num_filters'] (config.py:30) = 44 */
+    int32_t filter_sizes[4]; /* config.MODEL_MAP[..]['filter_sizes'] (config.py:16) = 64,32,16,16 */
+    int32_t linear_layer_size; /* config.py:13 = 48 */
+    int32_t chunk_rows;      /* window starts evaluated per pass of the conv stack (0 = default 32768) */
+    int32_t fbank_preproc;   /* enum ld_fbank_preproc */
+    int32_t reserved[6];
+} ld_config;
+
+/* One named tensor of a checkpoint's state_dict (host memory, fp32, C-contiguous). */
+typedef struct ld_tensor {
+    const char* name;    /* e.g. "block2.0.shortcut.0.weight" */
+    const float* data;
+    int64_t numel;
+} ld_tensor;
+
+LD_API const char* ld_last_error(void);
+LD_API const char* ld_version(void);
+
+/* Fills *cfg with the resnet_base / FEAT defaults of the reference's config.py:9-31. */
+LD_API void ld_default_config(ld_config* cfg);
+
+/* Replaces: model construction + model.set_device(device) (segment_laughter.py:59-61). */
+LD_API int ld_create(int device, const ld_config* cfg, ld_ctx** out);
+LD_API void ld_destroy(ld_ctx* ctx);
+
+/* K1. Replaces lhotse Fbank(FbankConfig(num_filters=44, frame_shift=0.01)).extract as reached from
+ * cut.compute_features(extractor) (load_data.py:47-49, utils/utils.py:25).
+ * pcm_d: int16 mono 16 kHz samples of n_chan recordings laid end to end; chan_len[c] samples each (host
+ * array).  mel_d: (257, num_filters) fp32 filterbank matrix, row-major (runtime data so that either the
+ * Lhotse or the Kaldi bank can be matched).  feats_d: fp32 (sum_c T_c, num_filters), T_c =
+ * (chan_len[c] + 80) / 160 (snip_edges=False); frames_out (host, optional) receives T_c. */
+LD_API int ld_fbank_i16(ld_ctx* ctx, const int16_t* pcm_d, const int64_t* chan_len, int32_t n_chan,
+                 const float* mel_d, float* feats_d, int64_t* frames_out, void* stream);
+LD_API int64_t ld_fbank_num_frames(int64_t num_samples);
+
+/* Replaces model.load_state_dict(checkpoint['state_dict']); model.eval() (segment_laughter.py:63-72):
+ * folds every BatchNorm's running statistics into a per-channel scale/shift and repacks the conv
+ * weights into the tensor-core operand layout.  Needs the 150 state_dict entries of ResNetBigger
+ * (num_batches_tracked entries may be omitted). */
+LD_API int ld_resnet_load_weights(ld_ctx* ctx, const ld_tensor* tensors, int32_t n);
+
+/* K2+K3. Replaces the whole inference loop of load_and_pred (segment_laughter.py:90-100) together with
+ * InferenceDataset windowing (datasets.py:82-93): for every frame i of every channel, the sigmoid
+ * output of ResNetBigger on feats[i:i+100] zero-padded at the tail.
+ * feats_d: fp32 (sum_c chan_frames[c], num_filters); probs_d: fp32 (sum_c chan_frames[c]). */
+LD_API int ld_resnet_infer_windows(ld_ctx* ctx, const float* feats_d, const int64_t* chan_frames, int32_t n_chan,
+                            float* probs_d, void* stream);
+
+/* K4. Replaces the run detection of laugh_segmenter.get_laughter_instances (laugh_segmenter.py:87-105)
+ * for n_thr thresholds at once: maximal runs of fix_over_underflow(p) > thr inside each channel, as
+ * (first_frame, last_frame) pairs relative to the channel start.  prob_is_f64: probs_d holds doubles.
+ * thr_cmp[k] is the value in-range probabilities are compared with and thr_raw[k] the value the clamped
+ * constants 1 and 1e-7 are compared with (they differ only when emulating NumPy>=2 float32 scalar
+ * comparison, see laugh_segmenter.py in the host mirror).
+ * Outputs (device): starts_d/ends_d int32 [n_thr][cap] per-threshold lists in frame order,
+ * chan_d int32 [n_thr][cap] channel index of each run, counts_d int32 [n_thr] (may exceed cap: the
+ * caller must then retry with a larger cap). */
+LD_API int ld_segment_runs(ld_ctx* ctx, const void* probs_d, int32_t prob_is_f64, const int64_t* chan_frames,
+                    int32_t n_chan, const double* thr_cmp, const double* thr_raw, int32_t n_thr,
+                    int32_t* starts_d, int32_t* ends_d, int32_t* chan_d, int32_t* counts_d, int32_t cap,
+                    void* stream);
+
+/* Host helper: the float64 time conversion and strict min-length filter of
+ * laugh_segmenter.py:23-24,104-108: keep (s/fps, e/fps) iff e/fps - s/fps > min_len. Returns #kept. */
+LD_API int64_t ld_filter_min_length(const int32_t* starts, const int32_t* ends, int64_t n, double fps,
+                             double min_len, double* out_start_s, double* out_end_s);
+
+/* K5. Replaces laugh_segmenter.lowpass = scipy.signal.filtfilt(b, a, sig) for a second-order section
+ * (laugh_segmenter.py:49-55; padtype='odd', padlen=9, lfilter_zi initial state).  b, a: 3 doubles each
+ * (host).  probs_d fp32 or fp64 (prob_is_f64) of length n; out_d: fp64 length n. */
+LD_API int ld_lowpass_filtfilt(ld_ctx* ctx, const void* probs_d, int32_t prob_is_f64, int64_t n, const double* b,
+                        const double* a, double* out_d, void* stream);
+/* Host helper: scipy.signal.butter(2, cutoff) coefficients (laugh_segmenter.py:52). */
+LD_API void ld_butter2_lowpass(double cutoff, double* b3, double* a3);
+
+/* End-to-end convenience used by segment_laughter / bench: host int16 PCM in, per-frame probabilities
+ * out (host), H2D and D2H copies included.  Equivalent to ld_fbank_i16 + ld_resnet_infer_windows. */
+LD_API int ld_infer_pcm_host(ld_ctx* ctx, const int16_t* pcm_host, const int64_t* chan_len, int32_t n_chan,
+                      const float* mel_host, float* probs_host, void* stream);
+
+/* Introspection (no GPU needed): JSON description of the streaming plan (planes, conv jobs, taps),
+ * consumed by tests/ to check the planner against the reference network on the CPU.  Returns the number
+ * of bytes required (including the terminating NUL); writes at most cap bytes. */
+LD_API int64_t ld_plan_json(const ld_config* cfg, char* buf, int64_t cap);
+
+/* Debug: copy one activation plane of the last processed chunk to the host as fp32 [rows][wp][C]. */
+LD_API int ld_debug_read_plane(ld_ctx* ctx, int32_t plane_id, int64_t rows, float* out_host);
+/* Executed multiply-accumulates per sequence row of the streaming plan, and kernel launches so far. */
+LD_API double ld_plan_macs_per_row(const ld_ctx* ctx);
+LD_API int64_t ld_kernel_launches(const ld_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LD_B200_H_ */

@@ -1,0 +1,120 @@
+"""ctypes binding of lib/libld_b200.so (C ABI declared in include/ld_b200.h).
+
+The library is the product; there is no Python/CPU fallback.  Importing this module only needs the
+shared object to exist (it is built in-tree by ``python -m laughter_detection_icsi_b200.build``);
+creating a context needs a B200.
+"""
+import ctypes
+import json
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libld_b200.so")
+
+LD_PREPROC_UTTERANCE = 0
+LD_PREPROC_FRAME = 1
+
+
+class LdError(RuntimeError):
+    pass
+
+
+class LdConfig(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", c_int32),
+        ("num_frames", c_int32),
+        ("num_filters", c_int32),
+        ("filter_sizes", c_int32 * 4),
+        ("linear_layer_size", c_int32),
+        ("chunk_rows", c_int32),
+        ("fbank_preproc", c_int32),
+        ("reserved", c_int32 * 6),
+    ]
+
+
+class LdTensor(ctypes.Structure):
+    _fields_ = [("name", c_char_p), ("data", POINTER(ctypes.c_float)), ("numel", c_int64)]
+
+
+# name -> (restype, argtypes); mirrors include/ld_b200.h one to one (checked by tests/test_abi.py)
+SIGNATURES = {
+    "ld_last_error": (c_char_p, []),
+    "ld_version": (c_char_p, []),
+    "ld_default_config": (None, [POINTER(LdConfig)]),
+    "ld_create": (c_int, [c_int, POINTER(LdConfig), POINTER(c_void_p)]),
+    "ld_destroy": (None, [c_void_p]),
+    "ld_fbank_i16": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_void_p, POINTER(c_int64), c_void_p]),
+    "ld_fbank_num_frames": (c_int64, [c_int64]),
+    "ld_resnet_load_weights": (c_int, [c_void_p, POINTER(LdTensor), c_int32]),
+    "ld_resnet_infer_windows": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_void_p]),
+    "ld_segment_runs": (c_int, [c_void_p, c_void_p, c_int32, POINTER(c_int64), c_int32, POINTER(c_double), POINTER(c_double),
+                                c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "ld_filter_min_length": (c_int64, [POINTER(c_int32), POINTER(c_int32), c_int64, c_double, c_double,
+                                       POINTER(c_double), POINTER(c_double)]),
+    "ld_lowpass_filtfilt": (c_int, [c_void_p, c_void_p, c_int32, c_int64, POINTER(c_double), POINTER(c_double), c_void_p, c_void_p]),
+    "ld_butter2_lowpass": (None, [c_double, POINTER(c_double), POINTER(c_double)]),
+    "ld_infer_pcm_host": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_void_p, c_void_p]),
+    "ld_plan_json": (c_int64, [POINTER(LdConfig), c_char_p, c_int64]),
+    "ld_debug_read_plane": (c_int, [c_void_p, c_int32, c_int64, c_void_p]),
+    "ld_plan_macs_per_row": (c_double, [c_void_p]),
+    "ld_kernel_launches": (c_int64, [c_void_p]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LdError(
+            f"{LIB_PATH} is missing: build the CUDA extension first "
+            "(python -m laughter_detection_icsi_b200.build). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        raise LdError(f"ld_b200 error {status}: {load_library().ld_last_error().decode()}")
+
+
+def default_config(**overrides):
+    cfg = LdConfig()
+    load_library().ld_default_config(ctypes.byref(cfg))
+    for k, v in overrides.items():
+        if k == "filter_sizes":
+            for i, f in enumerate(v):
+                cfg.filter_sizes[i] = int(f)
+        else:
+            setattr(cfg, k, int(v))
+    return cfg
+
+
+def plan_json(cfg=None):
+    """The streaming plan as a dict (planner only; runs without a GPU)."""
+    lib = load_library()
+    cfg = cfg if cfg is not None else default_config()
+    need = lib.ld_plan_json(ctypes.byref(cfg), None, 0)
+    if need < 0:
+        raise LdError(lib.ld_last_error().decode())
+    buf = ctypes.create_string_buffer(need)
+    lib.ld_plan_json(ctypes.byref(cfg), buf, need)
+    return json.loads(buf.value.decode())
+
+
+def i64_array(values):
+    arr = (c_int64 * len(values))(*[int(v) for v in values])
+    return arr
+
+
+def f64_array(values):
+    return (c_double * len(values))(*[float(v) for v in values])

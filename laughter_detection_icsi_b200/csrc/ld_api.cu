@@ -1,0 +1,659 @@
+// C ABI of the B200 laughter-detection hot path (include/ld_b200.h): context, workspace, weight
+// folding/packing, and the orchestration of the kernels in ld_fbank.cu / ld_net.cu / ld_gemm.cu /
+// ld_segment.cu.  No CPU fallback exists: every compute entry point launches CUDA kernels or fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/ld_b200.h"
+#include "ld_net.h"
+#include "ld_types.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define LD_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(LD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));              \
+    } while (0)
+
+struct PlaneDev {
+    __half* base = nullptr;  // pixel 0 of chunk 0
+    long long kc_stride = 0;
+    long long pixels_alloc = 0;
+    int C = 0, wp = 0;
+};
+
+struct ConvWeights {
+    __half* w = nullptr;
+    float* scale = nullptr;
+    float* shift = nullptr;
+    int cin = 0, cout = 0, ksize = 0;
+    std::string conv, bn;
+};
+
+struct ConvLaunchDev {
+    ld::GemmLaunch h;
+    ld::GemmLaunch* d = nullptr;
+    int wp = 0;
+};
+
+struct DeviceBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return LD_OK;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) return fail(LD_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        bytes = need;
+        return LD_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+}  // namespace
+
+struct ld_ctx {
+    int device = 0;
+    int num_sms = 148;
+    ld_config cfg{};
+    ld::NetConfig net;
+    ld::Plan plan;
+    int chunk_rows = 0;   // window starts per pass
+    int rows_alloc = 0;   // rows per plane (chunk_rows + H)
+    uint8_t* workspace = nullptr;
+    size_t workspace_bytes = 0;
+    std::vector<PlaneDev> planes;
+    std::map<std::string, ConvWeights> weights;
+    std::vector<ConvLaunchDev> convs;
+    ld::StemLaunch stem{};
+    ld::HeadLaunch head{};
+    float* stem_params = nullptr;  // w[576] scale[64] shift[64]
+    float* head_params = nullptr;
+    int head_param_count = 0;
+    bool weights_loaded = false;
+    // fbank
+    float* fbank_tables = nullptr;
+    std::vector<float> mel_host;
+    DeviceBuf mel_sparse;  // weights | lo | len | off
+    ld::FbankMel mel{};
+    unsigned long long* pcm_sum = nullptr;
+    // scratch
+    DeviceBuf chan_table, seg_scratch, iir_scratch, thr_buf;
+    DeviceBuf e2e_pcm, e2e_feats, e2e_probs, e2e_mel;
+    long long launches = 0;
+};
+
+namespace {
+
+void config_to_net(const ld_config& c, ld::NetConfig& n) {
+    n.H = c.num_frames; n.W = c.num_filters;
+    for (int i = 0; i < 4; ++i) n.filters[i] = c.filter_sizes[i];
+    n.linear_in = c.linear_layer_size;
+}
+
+int validate_config(const ld_config& c) {
+    if (c.num_frames != 100 || c.num_filters != 44)
+        return fail(LD_ERR_UNSUPPORTED, "only config.FEAT = {num_samples: 100, num_filters: 44} is supported");
+    for (int i = 0; i < 4; ++i)
+        if (c.filter_sizes[i] % 16 != 0 || c.filter_sizes[i] < 16 || c.filter_sizes[i] > 64)
+            return fail(LD_ERR_UNSUPPORTED, "filter_sizes must be multiples of 16 in [16, 64]");
+    if (c.filter_sizes[0] != 64) return fail(LD_ERR_UNSUPPORTED, "block1 must keep 64 channels (identity shortcut)");
+    return LD_OK;
+}
+
+int upload_channel_table(ld_ctx* ctx, const int64_t* frames, int n_chan, int gap, ld::ChannelTable& ct,
+                         long long& seq_total, long long& feat_total, cudaStream_t stream) {
+    std::vector<long long> h(3 * static_cast<size_t>(n_chan));
+    long long so = 0, fo = 0;
+    for (int c = 0; c < n_chan; ++c) {
+        if (frames[c] < 0) return fail(LD_ERR_INVALID, "negative channel length");
+        h[c] = so; h[n_chan + c] = frames[c]; h[2 * n_chan + c] = fo;
+        so += frames[c] + gap; fo += frames[c];
+    }
+    seq_total = so; feat_total = fo;
+    if (int r = ctx->chan_table.ensure(h.size() * sizeof(long long))) return r;
+    LD_CUDA(cudaMemcpyAsync(ctx->chan_table.p, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    LD_CUDA(cudaStreamSynchronize(stream));  // h is a stack-owned staging vector
+    const long long* d = static_cast<const long long*>(ctx->chan_table.p);
+    ct.seq_off = d; ct.frames = d + n_chan; ct.feat_off = d + 2 * n_chan; ct.n_chan = n_chan;
+    return LD_OK;
+}
+
+const ld_tensor* find_tensor(const ld_tensor* t, int n, const std::string& name) {
+    for (int i = 0; i < n; ++i)
+        if (t[i].name && name == t[i].name) return &t[i];
+    return nullptr;
+}
+
+// BatchNorm (eval) folded with the preceding conv/linear bias: y = scale * x + shift.
+int fold_bn(const ld_tensor* t, int n, const std::string& bn, const float* bias, int C, std::vector<float>& scale,
+            std::vector<float>& shift) {
+    const ld_tensor* g = find_tensor(t, n, bn + ".weight");
+    const ld_tensor* b = find_tensor(t, n, bn + ".bias");
+    const ld_tensor* m = find_tensor(t, n, bn + ".running_mean");
+    const ld_tensor* v = find_tensor(t, n, bn + ".running_var");
+    if (!g || !b || !m || !v) return fail(LD_ERR_INVALID, "state_dict is missing BatchNorm tensors of " + bn);
+    if (g->numel != C || b->numel != C || m->numel != C || v->numel != C)
+        return fail(LD_ERR_INVALID, "BatchNorm " + bn + " has the wrong size");
+    scale.resize(C); shift.resize(C);
+    for (int c = 0; c < C; ++c) {
+        const double s = static_cast<double>(g->data[c]) / std::sqrt(static_cast<double>(v->data[c]) + 1e-5);
+        scale[c] = static_cast<float>(s);
+        shift[c] = static_cast<float>(static_cast<double>(b->data[c]) +
+                                      s * ((bias ? static_cast<double>(bias[c]) : 0.0) - static_cast<double>(m->data[c])));
+    }
+    return LD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ld_last_error(void) { return g_err.c_str(); }
+const char* ld_version(void) { return "ld_b200 0.1 (sm_100a)"; }
+
+void ld_default_config(ld_config* cfg) {
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = sizeof(ld_config);
+    cfg->num_frames = 100;
+    cfg->num_filters = 44;
+    cfg->filter_sizes[0] = 64; cfg->filter_sizes[1] = 32; cfg->filter_sizes[2] = 16; cfg->filter_sizes[3] = 16;
+    cfg->linear_layer_size = 48;
+    cfg->chunk_rows = 0;
+    cfg->fbank_preproc = LD_PREPROC_UTTERANCE;
+}
+
+int64_t ld_plan_json(const ld_config* cfg, char* buf, int64_t cap) {
+    try {
+        ld_config c;
+        if (cfg) c = *cfg; else ld_default_config(&c);
+        if (validate_config(c)) return -1;
+        ld::NetConfig net;
+        config_to_net(c, net);
+        const std::string s = ld::plan_to_json(ld::build_stream_plan(net));
+        const int64_t need = static_cast<int64_t>(s.size()) + 1;
+        if (buf && cap > 0) {
+            const int64_t n = std::min<int64_t>(need, cap);
+            std::memcpy(buf, s.c_str(), static_cast<size_t>(n - 1));
+            buf[n - 1] = 0;
+        }
+        return need;
+    } catch (const std::exception& e) {
+        fail(LD_ERR_INVALID, e.what());
+        return -1;
+    }
+}
+
+int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
+    if (!out) return fail(LD_ERR_INVALID, "out is null");
+    *out = nullptr;
+    ld_config cfg;
+    if (cfg_in) cfg = *cfg_in; else ld_default_config(&cfg);
+    if (int r = validate_config(cfg)) return r;
+    int count = 0;
+    LD_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(LD_ERR_INVALID, "no such CUDA device");
+    LD_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LD_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(LD_ERR_UNSUPPORTED, std::string("this library is built for sm_100a (B200) only; found ") + prop.name);
+
+    ld_ctx* ctx = new ld_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->cfg = cfg;
+    config_to_net(cfg, ctx->net);
+    try {
+        ctx->plan = ld::build_stream_plan(ctx->net);
+    } catch (const std::exception& e) {
+        delete ctx;
+        return fail(LD_ERR_INVALID, e.what());
+    }
+    const ld::Plan& plan = ctx->plan;
+    ctx->chunk_rows = cfg.chunk_rows > 0 ? cfg.chunk_rows : 32768;
+    ctx->rows_alloc = ctx->chunk_rows + plan.H;
+
+    auto cleanup_fail = [&](int code) { ld_destroy(ctx); return code; };
+#define LD_CUDA_C(expr)                                                                                  \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return cleanup_fail(fail(LD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__))); \
+    } while (0)
+
+    // ---- workspace: every plane gets its own zero-initialised allocation with guard pixels ------------
+    ctx->planes.resize(plan.planes.size());
+    size_t total = 0;
+    std::vector<size_t> offs(plan.planes.size());
+    for (size_t i = 0; i < plan.planes.size(); ++i) {
+        const auto& ps = plan.planes[i];
+        PlaneDev& pd = ctx->planes[i];
+        const long long guard = static_cast<long long>(ld::kGuardRows) * ps.wp + 256;
+        pd.C = ps.C; pd.wp = ps.wp;
+        pd.pixels_alloc = static_cast<long long>(ctx->rows_alloc) * ps.wp + 2 * guard;
+        pd.kc_stride = pd.pixels_alloc * 8;
+        offs[i] = total;
+        total += static_cast<size_t>(pd.pixels_alloc) * 16 * (ps.C / 8);
+        total = (total + 255) & ~static_cast<size_t>(255);
+    }
+    ctx->workspace_bytes = total;
+    LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->workspace), total));
+    LD_CUDA_C(cudaMemset(ctx->workspace, 0, total));
+    for (size_t i = 0; i < plan.planes.size(); ++i) {
+        const long long guard = static_cast<long long>(ld::kGuardRows) * plan.planes[i].wp + 256;
+        ctx->planes[i].base = reinterpret_cast<__half*>(ctx->workspace + offs[i]) + guard * 8;
+    }
+
+    // ---- weights (allocated now so that launch tables can point at them; filled by load_weights) -----
+    for (const auto& cs : plan.convs) {
+        if (ctx->weights.count(cs.conv)) continue;
+        ConvWeights w;
+        w.cin = cs.cin; w.cout = cs.cout; w.ksize = cs.ksize; w.conv = cs.conv; w.bn = cs.bn;
+        const size_t n = static_cast<size_t>(cs.ksize) * cs.ksize * cs.cin * cs.cout;
+        LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&w.w), n * sizeof(__half)));
+        LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&w.scale), cs.cout * sizeof(float)));
+        LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&w.shift), cs.cout * sizeof(float)));
+        ctx->weights[cs.conv] = w;
+    }
+    LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->stem_params), (576 + 128) * sizeof(float)));
+    const int F = cfg.linear_layer_size;
+    if (F > ld::kMaxHeadFeat) return cleanup_fail(fail(LD_ERR_UNSUPPORTED, "linear_layer_size too large"));
+    ctx->head_param_count = 2 * F + 32 * F + 32 + 64 + 32 + 1;
+    LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->head_params), ctx->head_param_count * sizeof(float)));
+
+    // ---- launch tables -----------------------------------------------------------------------------------
+    ctx->convs.resize(plan.convs.size());
+    for (size_t li = 0; li < plan.convs.size(); ++li) {
+        const auto& cs = plan.convs[li];
+        ConvLaunchDev& cd = ctx->convs[li];
+        ld::GemmLaunch& L = cd.h;
+        std::memset(&L, 0, sizeof(L));
+        const ConvWeights& w = ctx->weights[cs.conv];
+        L.weights = w.w; L.scale = w.scale; L.shift = w.shift;
+        L.n_jobs = static_cast<int>(cs.jobs.size());
+        L.cin = cs.cin; L.cout = cs.cout; L.n_wtaps = cs.ksize * cs.ksize;
+        L.relu = cs.relu; L.wp = cs.wp; L.out_mode = cs.out_mode; L.wp2 = cs.wp2; L.hp = cs.hp;
+        cd.wp = cs.wp;
+        int ext_max = 0;
+        for (int j = 0; j < L.n_jobs; ++j) {
+            const auto& js = cs.jobs[j];
+            ld::GemmJob& job = L.jobs[j];
+            std::vector<ld::TapSpec> taps = js.taps;
+            std::sort(taps.begin(), taps.end(), [](const ld::TapSpec& a, const ld::TapSpec& b) {
+                return a.plane != b.plane ? a.plane < b.plane : a.shift < b.shift;
+            });
+            if (taps.size() > static_cast<size_t>(ld::kMaxTaps)) return cleanup_fail(fail(LD_ERR_INVALID, "too many taps"));
+            int g = -1, g_plane = -1, g_min = 0;
+            for (size_t t = 0; t < taps.size(); ++t) {
+                if (g < 0 || taps[t].plane != g_plane || taps[t].shift - g_min > 136) {
+                    if (++g >= ld::kMaxGroups) return cleanup_fail(fail(LD_ERR_INVALID, "too many load groups"));
+                    g_plane = taps[t].plane; g_min = taps[t].shift;
+                    job.groups[g].src = ctx->planes[g_plane].base;
+                    job.groups[g].kc_stride = ctx->planes[g_plane].kc_stride;
+                    job.groups[g].shift = g_min;
+                    job.groups[g].ext = ld::kTileM;
+                    if (ctx->planes[g_plane].C != cs.cin || ctx->planes[g_plane].wp != cs.wp)
+                        return cleanup_fail(fail(LD_ERR_INVALID, "plan/plane mismatch in " + cs.conv));
+                }
+                job.groups[g].ext = std::max(job.groups[g].ext, ld::kTileM + taps[t].shift - g_min);
+                job.taps[t].group = static_cast<int16_t>(g);
+                job.taps[t].off = static_cast<int16_t>(taps[t].shift - g_min);
+                job.taps[t].wtap = static_cast<int16_t>(taps[t].wtap);
+            }
+            job.n_groups = g + 1;
+            job.n_taps = static_cast<int>(taps.size());
+            for (int q = 0; q < job.n_groups; ++q) ext_max = std::max(ext_max, job.groups[q].ext);
+            job.out0 = ctx->planes[js.out0].base;
+            job.out1 = js.out1 >= 0 ? ctx->planes[js.out1].base : nullptr;
+            job.out_kc_stride = ctx->planes[js.out0].kc_stride;
+            if (js.res_plane >= 0) {
+                job.res = ctx->planes[js.res_plane].base;
+                job.res_kc_stride = ctx->planes[js.res_plane].kc_stride;
+                job.res_shift = js.res_shift;
+            }
+        }
+        L.ext_alloc = (ext_max + 7) & ~7;
+        L.n_stages = ld::gemm_pick_stages(L.cin, L.cout, L.n_wtaps, L.ext_alloc);
+        if (L.n_stages < 2) return cleanup_fail(fail(LD_ERR_INVALID, "conv " + cs.conv + " does not fit in shared memory"));
+        LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&cd.d), sizeof(ld::GemmLaunch)));
+        LD_CUDA_C(cudaMemcpy(cd.d, &L, sizeof(L), cudaMemcpyHostToDevice));
+    }
+    // stem
+    ctx->stem.n_jobs = static_cast<int>(plan.stem.size());
+    ctx->stem.W = plan.W;
+    if (ctx->stem.n_jobs > ld::kMaxStemJobs) return cleanup_fail(fail(LD_ERR_INVALID, "too many stem jobs"));
+    for (int j = 0; j < ctx->stem.n_jobs; ++j) {
+        const auto& sj = plan.stem[j];
+        ctx->stem.jobs[j].out = ctx->planes[sj.out_plane].base;
+        ctx->stem.jobs[j].kc_stride = ctx->planes[sj.out_plane].kc_stride;
+        ctx->stem.jobs[j].row_shift = sj.row_shift;
+        ctx->stem.jobs[j].mask = sj.mask;
+    }
+    ctx->stem.w = ctx->stem_params; ctx->stem.scale = ctx->stem_params + 576; ctx->stem.shift = ctx->stem_params + 640;
+    // head
+    ctx->head.n_feat = F; ctx->head.C = plan.head_C; ctx->head.groups = plan.head_pool_groups; ctx->head.wp = plan.head_wp;
+    ctx->head.params = ctx->head_params;
+    if (plan.head_rows.size() > static_cast<size_t>(ld::kMaxHeadRows)) return cleanup_fail(fail(LD_ERR_INVALID, "too many head rows"));
+    for (size_t i = 0; i < plan.head_rows.size(); ++i) {
+        ctx->head.rows[i].plane = ctx->planes[plan.head_rows[i].plane].base;
+        ctx->head.rows[i].kc_stride = ctx->planes[plan.head_rows[i].plane].kc_stride;
+        ctx->head.rows[i].row_shift = plan.head_rows[i].row_shift;
+    }
+    // fbank tables
+    {
+        std::vector<float> tab(ld::kFbankTableFloats);
+        ld::fbank_host_tables(tab.data());
+        LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->fbank_tables), tab.size() * sizeof(float)));
+        LD_CUDA_C(cudaMemcpy(ctx->fbank_tables, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+        LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->pcm_sum), sizeof(unsigned long long) * 1024));
+    }
+    if (std::getenv("LD_VERBOSE"))
+        std::fprintf(stderr, "ld_b200: %zu planes, workspace %.2f GB, %zu conv launches, %.1f MMAC/row, chunk %d rows\n",
+                     plan.planes.size(), total / 1e9, plan.convs.size(), plan.macs_per_row / 1e6, ctx->chunk_rows);
+#undef LD_CUDA_C
+    *out = ctx;
+    return LD_OK;
+}
+
+void ld_destroy(ld_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->workspace) cudaFree(ctx->workspace);
+    for (auto& kv : ctx->weights) {
+        if (kv.second.w) cudaFree(kv.second.w);
+        if (kv.second.scale) cudaFree(kv.second.scale);
+        if (kv.second.shift) cudaFree(kv.second.shift);
+    }
+    for (auto& c : ctx->convs) if (c.d) cudaFree(c.d);
+    if (ctx->stem_params) cudaFree(ctx->stem_params);
+    if (ctx->head_params) cudaFree(ctx->head_params);
+    if (ctx->fbank_tables) cudaFree(ctx->fbank_tables);
+    if (ctx->pcm_sum) cudaFree(ctx->pcm_sum);
+    ctx->mel_sparse.release(); ctx->chan_table.release(); ctx->seg_scratch.release(); ctx->iir_scratch.release();
+    ctx->thr_buf.release(); ctx->e2e_pcm.release(); ctx->e2e_feats.release(); ctx->e2e_probs.release(); ctx->e2e_mel.release();
+    delete ctx;
+}
+
+int ld_resnet_load_weights(ld_ctx* ctx, const ld_tensor* t, int32_t n) {
+    if (!ctx || !t || n <= 0) return fail(LD_ERR_INVALID, "bad arguments");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    std::vector<float> scale, shift;
+    // stem: conv1 (64,1,3,3) no bias + bn1
+    {
+        const ld_tensor* w = find_tensor(t, n, "conv1.weight");
+        if (!w || w->numel != 576) return fail(LD_ERR_INVALID, "state_dict is missing conv1.weight (64,1,3,3)");
+        if (int r = fold_bn(t, n, "bn1", nullptr, 64, scale, shift)) return r;
+        std::vector<float> p(576 + 128);
+        std::memcpy(p.data(), w->data, 576 * sizeof(float));
+        std::memcpy(p.data() + 576, scale.data(), 64 * sizeof(float));
+        std::memcpy(p.data() + 640, shift.data(), 64 * sizeof(float));
+        LD_CUDA(cudaMemcpy(ctx->stem_params, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    for (auto& kv : ctx->weights) {
+        ConvWeights& cw = kv.second;
+        const ld_tensor* w = find_tensor(t, n, cw.conv + ".weight");
+        const ld_tensor* b = find_tensor(t, n, cw.conv + ".bias");
+        const int taps = cw.ksize * cw.ksize;
+        if (!w || w->numel != static_cast<int64_t>(taps) * cw.cin * cw.cout)
+            return fail(LD_ERR_INVALID, "state_dict is missing or mis-sized: " + cw.conv + ".weight");
+        if (b && b->numel != cw.cout) return fail(LD_ERR_INVALID, "mis-sized " + cw.conv + ".bias");
+        if (int r = fold_bn(t, n, cw.bn, b ? b->data : nullptr, cw.cout, scale, shift)) return r;
+        // (out, in, kh, kw) fp32 -> [tap][in/8][out][8] fp16: the K-major SWIZZLE_NONE B operand
+        std::vector<__half> packed(static_cast<size_t>(taps) * cw.cin * cw.cout);
+        for (int tap = 0; tap < taps; ++tap)
+            for (int kc = 0; kc < cw.cin / 8; ++kc)
+                for (int o = 0; o < cw.cout; ++o)
+                    for (int e = 0; e < 8; ++e) {
+                        const int i = kc * 8 + e;
+                        const float v = w->data[(static_cast<size_t>(o) * cw.cin + i) * taps + tap];
+                        packed[((static_cast<size_t>(tap) * (cw.cin / 8) + kc) * cw.cout + o) * 8 + e] = __float2half_rn(v);
+                    }
+        LD_CUDA(cudaMemcpy(cw.w, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        LD_CUDA(cudaMemcpy(cw.scale, scale.data(), cw.cout * sizeof(float), cudaMemcpyHostToDevice));
+        LD_CUDA(cudaMemcpy(cw.shift, shift.data(), cw.cout * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    // head: bn2 -> linear1 -> bn3 -> relu -> linear2 -> sigmoid
+    {
+        const int F = ctx->cfg.linear_layer_size;
+        const ld_tensor* w1 = find_tensor(t, n, "linear1.weight");
+        const ld_tensor* b1 = find_tensor(t, n, "linear1.bias");
+        const ld_tensor* w2 = find_tensor(t, n, "linear2.weight");
+        const ld_tensor* b2 = find_tensor(t, n, "linear2.bias");
+        if (!w1 || !b1 || !w2 || !b2 || w1->numel != 32 * F || b1->numel != 32 || w2->numel != 32 || b2->numel != 1)
+            return fail(LD_ERR_INVALID, "state_dict is missing or mis-sized linear1/linear2 tensors");
+        std::vector<float> p(ctx->head_param_count);
+        std::vector<float> s2, h2, s3, h3;
+        if (int r = fold_bn(t, n, "bn2", nullptr, F, s2, h2)) return r;
+        if (int r = fold_bn(t, n, "bn3", b1->data, 32, s3, h3)) return r;  // linear1 bias folded into bn3's shift
+        float* q = p.data();
+        std::memcpy(q, s2.data(), F * sizeof(float)); q += F;
+        std::memcpy(q, h2.data(), F * sizeof(float)); q += F;
+        std::memcpy(q, w1->data, 32 * F * sizeof(float)); q += 32 * F;
+        std::memset(q, 0, 32 * sizeof(float)); q += 32;  // b1 lives in bn3's shift
+        std::memcpy(q, s3.data(), 32 * sizeof(float)); q += 32;
+        std::memcpy(q, h3.data(), 32 * sizeof(float)); q += 32;
+        std::memcpy(q, w2->data, 32 * sizeof(float)); q += 32;
+        *q = b2->data[0];
+        LD_CUDA(cudaMemcpy(ctx->head_params, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    ctx->weights_loaded = true;
+    return LD_OK;
+}
+
+int ld_resnet_infer_windows(ld_ctx* ctx, const float* feats_d, const int64_t* chan_frames, int32_t n_chan, float* probs_d,
+                            void* stream_v) {
+    if (!ctx || !feats_d || !chan_frames || !probs_d || n_chan <= 0) return fail(LD_ERR_INVALID, "bad arguments");
+    if (!ctx->weights_loaded) return fail(LD_ERR_STATE, "ld_resnet_load_weights has not been called");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    ld::ChannelTable ct;
+    long long seq_total = 0, feat_total = 0;
+    const int H = ctx->plan.H;
+    if (int r = upload_channel_table(ctx, chan_frames, n_chan, H, ct, seq_total, feat_total, stream)) return r;
+    for (long long row0 = 0; row0 < seq_total; row0 += ctx->chunk_rows) {
+        const int nb = static_cast<int>(std::min<long long>(ctx->chunk_rows, seq_total - row0));
+        const int rows = nb + H;
+        LD_CUDA(ld::launch_stem(ctx->stem, ct, feats_d, row0, rows, stream));
+        ++ctx->launches;
+        for (auto& cd : ctx->convs) {
+            const int M = rows * cd.wp;
+            const int m_tiles = (M + ld::kTileM - 1) / ld::kTileM;
+            LD_CUDA(ld::launch_gemm_taps(cd.d, cd.h, m_tiles, M, ctx->num_sms, stream));
+            ++ctx->launches;
+        }
+        LD_CUDA(ld::launch_head(ctx->head, ct, probs_d, row0, nb, stream));
+        ++ctx->launches;
+    }
+    return LD_OK;
+}
+
+int64_t ld_fbank_num_frames(int64_t num_samples) { return (num_samples + 80) / 160; }
+
+int ld_fbank_i16(ld_ctx* ctx, const int16_t* pcm_d, const int64_t* chan_len, int32_t n_chan, const float* mel_d,
+                 float* feats_d, int64_t* frames_out, void* stream_v) {
+    if (!ctx || !pcm_d || !chan_len || !mel_d || !feats_d || n_chan <= 0) return fail(LD_ERR_INVALID, "bad arguments");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const int F = ctx->cfg.num_filters;
+    // sparse view of the filterbank (rebuilt only when the matrix changes)
+    {
+        std::vector<float> m(257 * static_cast<size_t>(F));
+        LD_CUDA(cudaMemcpyAsync(m.data(), mel_d, m.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        LD_CUDA(cudaStreamSynchronize(stream));
+        if (m != ctx->mel_host) {
+            std::vector<float> w;
+            std::vector<int> lo(F), len(F), off(F);
+            for (int k = 0; k < F; ++k) {
+                int a = -1, b = -1;
+                for (int j = 0; j < 257; ++j)
+                    if (m[static_cast<size_t>(j) * F + k] != 0.f) { if (a < 0) a = j; b = j; }
+                if (a < 0) { a = 0; b = 0; }
+                lo[k] = a; len[k] = b - a + 1; off[k] = static_cast<int>(w.size());
+                for (int j = a; j <= b; ++j) w.push_back(m[static_cast<size_t>(j) * F + k]);
+            }
+            if (w.size() > 1024 || F > 64) return fail(LD_ERR_UNSUPPORTED, "filterbank has too many non-zero weights");
+            const size_t bytes = w.size() * sizeof(float) + 3 * F * sizeof(int);
+            if (int r = ctx->mel_sparse.ensure(bytes)) return r;
+            uint8_t* d = static_cast<uint8_t*>(ctx->mel_sparse.p);
+            LD_CUDA(cudaMemcpy(d, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+            int* di = reinterpret_cast<int*>(d + w.size() * sizeof(float));
+            LD_CUDA(cudaMemcpy(di, lo.data(), F * sizeof(int), cudaMemcpyHostToDevice));
+            LD_CUDA(cudaMemcpy(di + F, len.data(), F * sizeof(int), cudaMemcpyHostToDevice));
+            LD_CUDA(cudaMemcpy(di + 2 * F, off.data(), F * sizeof(int), cudaMemcpyHostToDevice));
+            ctx->mel.weights = reinterpret_cast<const float*>(d);
+            ctx->mel.lo = di; ctx->mel.len = di + F; ctx->mel.off = di + 2 * F; ctx->mel.n_filters = F;
+            ctx->mel_host = m;
+        }
+    }
+    const int per_frame = ctx->cfg.fbank_preproc == LD_PREPROC_FRAME;
+    long long s_off = 0, f_off = 0;
+    for (int c = 0; c < n_chan; ++c) {
+        const long long L = chan_len[c];
+        if (L < 200) return fail(LD_ERR_UNSUPPORTED, "recordings shorter than 200 samples are not supported");
+        const long long T = (L + 80) / 160;
+        unsigned long long* sum = ctx->pcm_sum + (c & 1023);
+        if (!per_frame) {
+            LD_CUDA(ld::launch_pcm_sum(pcm_d + s_off, L, sum, stream));
+            ++ctx->launches;
+        }
+        LD_CUDA(ld::launch_fbank(pcm_d + s_off, L, T, sum, per_frame, ctx->mel, ctx->fbank_tables, feats_d + f_off * F, stream));
+        ++ctx->launches;
+        if (frames_out) frames_out[c] = T;
+        s_off += L; f_off += T;
+    }
+    return LD_OK;
+}
+
+int ld_segment_runs(ld_ctx* ctx, const void* probs_d, int32_t prob_is_f64, const int64_t* chan_frames, int32_t n_chan,
+                    const double* thr_cmp, const double* thr_raw, int32_t n_thr, int32_t* starts_d, int32_t* ends_d,
+                    int32_t* chan_d, int32_t* counts_d, int32_t cap, void* stream_v) {
+    if (!ctx || !probs_d || !chan_frames || !thr_cmp || !thr_raw || !starts_d || !ends_d || !chan_d || !counts_d ||
+        n_chan <= 0 || n_thr <= 0 || cap < 0)
+        return fail(LD_ERR_INVALID, "bad arguments");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    ld::ChannelTable ct;
+    long long seq_total = 0, total = 0;
+    if (int r = upload_channel_table(ctx, chan_frames, n_chan, 0, ct, seq_total, total, stream)) return r;
+    if (total >= (1ll << 31)) return fail(LD_ERR_UNSUPPORTED, "more than 2^31 frames in one call");
+    if (int r = ctx->thr_buf.ensure(2 * sizeof(double) * n_thr)) return r;
+    double* thr_d = static_cast<double*>(ctx->thr_buf.p);
+    LD_CUDA(cudaMemcpyAsync(thr_d, thr_cmp, sizeof(double) * n_thr, cudaMemcpyHostToDevice, stream));
+    LD_CUDA(cudaMemcpyAsync(thr_d + n_thr, thr_raw, sizeof(double) * n_thr, cudaMemcpyHostToDevice, stream));
+    LD_CUDA(cudaStreamSynchronize(stream));
+    if (int r = ctx->seg_scratch.ensure(ld::segment_scratch_ints(total, n_thr) * sizeof(int))) return r;
+    LD_CUDA(ld::launch_segment_runs(probs_d, prob_is_f64, ct, total, thr_d, thr_d + n_thr, n_thr, starts_d, ends_d, chan_d,
+                                    counts_d, cap, static_cast<int*>(ctx->seg_scratch.p), stream));
+    ctx->launches += 3;
+    return LD_OK;
+}
+
+int64_t ld_filter_min_length(const int32_t* starts, const int32_t* ends, int64_t n, double fps, double min_len,
+                             double* out_start_s, double* out_end_s) {
+    int64_t kept = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        // frame_span_to_time_span: (frame / fps); filter: inst[1] - inst[0] > min_l   -- all IEEE double
+        const volatile double s = static_cast<double>(starts[i]) / fps;
+        const volatile double e = static_cast<double>(ends[i]) / fps;
+        const volatile double d = e - s;
+        if (d > min_len) {
+            if (out_start_s) out_start_s[kept] = s;
+            if (out_end_s) out_end_s[kept] = e;
+            ++kept;
+        }
+    }
+    return kept;
+}
+
+void ld_butter2_lowpass(double cutoff, double* b, double* a) {
+    // Bilinear-transformed 2nd-order Butterworth low-pass, Wn = cutoff (fraction of Nyquist).
+    const double pi = 3.14159265358979323846;
+    const double K = std::tan(pi * cutoff / 2.0);
+    const double norm = 1.0 / (1.0 + std::sqrt(2.0) * K + K * K);
+    b[0] = K * K * norm; b[1] = 2.0 * b[0]; b[2] = b[0];
+    a[0] = 1.0; a[1] = 2.0 * (K * K - 1.0) * norm; a[2] = (1.0 - std::sqrt(2.0) * K + K * K) * norm;
+}
+
+int ld_lowpass_filtfilt(ld_ctx* ctx, const void* probs_d, int32_t prob_is_f64, int64_t n, const double* b, const double* a,
+                        double* out_d, void* stream_v) {
+    if (!ctx || !probs_d || !b || !a || !out_d) return fail(LD_ERR_INVALID, "bad arguments");
+    if (n <= 9) return fail(LD_ERR_INVALID, "The length of the input vector x must be greater than padlen, which is 9.");
+    if (a[0] == 0.0) return fail(LD_ERR_INVALID, "a[0] must be non-zero");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (int r = ctx->iir_scratch.ensure(ld::filtfilt_scratch_doubles(n) * sizeof(double))) return r;
+    LD_CUDA(ld::launch_filtfilt(probs_d, prob_is_f64, n, b, a, out_d, static_cast<double*>(ctx->iir_scratch.p), stream));
+    ctx->launches += 6;
+    return LD_OK;
+}
+
+int ld_infer_pcm_host(ld_ctx* ctx, const int16_t* pcm_host, const int64_t* chan_len, int32_t n_chan, const float* mel_host,
+                      float* probs_host, void* stream_v) {
+    if (!ctx || !pcm_host || !chan_len || !mel_host || !probs_host || n_chan <= 0) return fail(LD_ERR_INVALID, "bad arguments");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const int F = ctx->cfg.num_filters;
+    long long samples = 0, frames = 0;
+    std::vector<int64_t> T(n_chan);
+    for (int c = 0; c < n_chan; ++c) {
+        samples += chan_len[c];
+        T[c] = (chan_len[c] + 80) / 160;
+        frames += T[c];
+    }
+    if (int r = ctx->e2e_pcm.ensure(samples * sizeof(int16_t))) return r;
+    if (int r = ctx->e2e_feats.ensure(frames * F * sizeof(float))) return r;
+    if (int r = ctx->e2e_probs.ensure(frames * sizeof(float))) return r;
+    if (int r = ctx->e2e_mel.ensure(257 * F * sizeof(float))) return r;
+    LD_CUDA(cudaMemcpyAsync(ctx->e2e_pcm.p, pcm_host, samples * sizeof(int16_t), cudaMemcpyHostToDevice, stream));
+    LD_CUDA(cudaMemcpyAsync(ctx->e2e_mel.p, mel_host, 257 * F * sizeof(float), cudaMemcpyHostToDevice, stream));
+    if (int r = ld_fbank_i16(ctx, static_cast<const int16_t*>(ctx->e2e_pcm.p), chan_len, n_chan,
+                             static_cast<const float*>(ctx->e2e_mel.p), static_cast<float*>(ctx->e2e_feats.p), nullptr, stream_v))
+        return r;
+    if (int r = ld_resnet_infer_windows(ctx, static_cast<const float*>(ctx->e2e_feats.p), T.data(), n_chan,
+                                        static_cast<float*>(ctx->e2e_probs.p), stream_v))
+        return r;
+    LD_CUDA(cudaMemcpyAsync(probs_host, ctx->e2e_probs.p, frames * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    LD_CUDA(cudaStreamSynchronize(stream));
+    return LD_OK;
+}
+
+int ld_debug_read_plane(ld_ctx* ctx, int32_t plane_id, int64_t rows, float* out_host) {
+    if (!ctx || !out_host || plane_id < 0 || plane_id >= static_cast<int>(ctx->planes.size()) || rows <= 0 ||
+        rows > ctx->rows_alloc)
+        return fail(LD_ERR_INVALID, "bad arguments");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    LD_CUDA(cudaDeviceSynchronize());
+    const PlaneDev& p = ctx->planes[plane_id];
+    const long long pixels = rows * p.wp;
+    std::vector<__half> h(static_cast<size_t>(pixels) * 8);
+    for (int kc = 0; kc < p.C / 8; ++kc) {
+        LD_CUDA(cudaMemcpy(h.data(), p.base + kc * p.kc_stride, h.size() * sizeof(__half), cudaMemcpyDeviceToHost));
+        for (long long px = 0; px < pixels; ++px)
+            for (int e = 0; e < 8; ++e) out_host[px * p.C + kc * 8 + e] = __half2float(h[px * 8 + e]);
+    }
+    return LD_OK;
+}
+
+double ld_plan_macs_per_row(const ld_ctx* ctx) { return ctx ? ctx->plan.macs_per_row : 0.0; }
+int64_t ld_kernel_launches(const ld_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

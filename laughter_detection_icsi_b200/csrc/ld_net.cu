@@ -1,0 +1,160 @@
+// K2a (stem) and K3 (head) of the streaming ResNetBigger evaluation, on CUDA cores in fp32.
+//
+//  stem:  conv1 (1->64, 3x3, pad 1, no bias) + bn1 + ReLU            reference models.py:186-191,224
+//         reads the fp32 log-mel features directly (no fp16 rounding of the network input) and writes
+//         the fp16 channel-chunk-planar planes the tensor-core convs consume.
+//  head:  AvgPool2d(4) -> view -> bn2 -> linear1 -> bn3 -> ReLU -> linear2 -> sigmoid
+//                                                                      reference models.py:229-238
+//         (dropout is the identity in eval mode).
+//
+// A "sequence" is the concatenation of channels with zero gaps; seq rows that fall into a gap or past
+// the end read as all-zero features, which is exactly InferenceDataset's right zero padding
+// (reference datasets.py:85-93).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "ld_net.h"
+
+namespace ld {
+
+// Channel of sequence row s, or -1 when s lies in a gap / outside. Binary search over seq_off.
+__device__ __forceinline__ int find_channel(const ChannelTable& ct, long long s, long long& local) {
+    if (s < 0) return -1;
+    int lo = 0, hi = ct.n_chan - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (ct.seq_off[mid] <= s) lo = mid; else hi = mid - 1;
+    }
+    local = s - ct.seq_off[lo];
+    return (local >= 0 && local < ct.frames[lo]) ? lo : -1;
+}
+
+__global__ void __launch_bounds__(256)
+stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long long chunk_row0, int rows) {
+    __shared__ float s_w[64 * 9];
+    __shared__ float s_scale[64], s_shift[64];
+    for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) s_w[i] = L.w[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) { s_scale[i] = L.scale[i]; s_shift[i] = L.shift[i]; }
+    __syncthreads();
+
+    const StemJob job = L.jobs[blockIdx.y];
+    const int wp = L.W + 2;
+    const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= static_cast<long long>(rows) * wp) return;
+    const long long r = p / wp;
+    const int col = static_cast<int>(p - r * wp) - 1;  // real column, -1 and W are padding
+    __half* out = job.out + p * 8;
+
+    if (col < 0 || col >= L.W) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(out + kc * job.kc_stride) = z;
+        return;
+    }
+    float x[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        long long local = 0;
+        const long long s = chunk_row0 + r + job.row_shift + ky - 1;
+        const int c = ((job.mask >> ky) & 1) ? find_channel(ct, s, local) : -1;
+        const float* frow = (c >= 0) ? feats + (ct.feat_off[c] + local) * L.W : nullptr;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int cc = col + kx - 1;
+            x[ky * 3 + kx] = (frow != nullptr && cc >= 0 && cc < L.W) ? __ldg(frow + cc) : 0.f;
+        }
+    }
+    for (int kc = 0; kc < 8; ++kc) {
+        uint4 ov;
+        __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float a[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int ch = kc * 8 + 2 * e + h;
+                float acc = 0.f;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) acc = fmaf(s_w[ch * 9 + t], x[t], acc);
+                a[h] = fmaxf(fmaf(acc, s_scale[ch], s_shift[ch]), 0.f);
+            }
+            oh[e] = __floats2half2_rn(a[0], a[1]);
+        }
+        *reinterpret_cast<uint4*>(out + kc * job.kc_stride) = ov;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+head_kernel(HeadLaunch L, ChannelTable ct, float* __restrict__ probs, long long chunk_row0, int nb) {
+    extern __shared__ float s_par[];
+    // layout: bn2 scale[F] shift[F] | W1[32*F] b1[32] | bn3 scale[32] shift[32] | w2[32] b2
+    const int F = L.n_feat;
+    const int n_par = 2 * F + 32 * F + 32 + 64 + 32 + 1;
+    for (int i = threadIdx.x; i < n_par; i += blockDim.x) s_par[i] = L.params[i];
+    __syncthreads();
+    const float* bn2_s = s_par;
+    const float* bn2_b = bn2_s + F;
+    const float* w1 = bn2_b + F;
+    const float* b1 = w1 + 32 * F;
+    const float* bn3_s = b1 + 32;
+    const float* bn3_b = bn3_s + 32;
+    const float* w2 = bn3_b + 32;
+    const float b2 = w2[32];
+
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    long long local = 0;
+    const int chan = find_channel(ct, chunk_row0 + b, local);
+    if (chan < 0) return;  // gap row: no window starts here
+
+    // AvgPool2d(4): rows 4g..4g+3, real cols 0..3; feature index = c * groups + g   (models.py:229-230)
+    float x[kMaxHeadFeat];
+    const int C = L.C, G = L.groups;
+    for (int i = 0; i < F; ++i) x[i] = 0.f;
+    for (int i = 0; i < 4 * G; ++i) {
+        const HeadRow hr = L.rows[i];
+        const __half* base = hr.plane + ((static_cast<long long>(b) + hr.row_shift) * L.wp + 1) * 8;
+        const int g = i >> 2;
+        for (int kc = 0; kc < C / 8; ++kc) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int cpx = 0; cpx < 4; ++cpx) {
+                const uint4 v = *reinterpret_cast<const uint4*>(base + kc * hr.kc_stride + cpx * 8);
+                const __half2* vh = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(vh[e]);
+                    acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[(kc * 8 + e) * G + g] += acc[e];
+        }
+    }
+    for (int i = 0; i < F; ++i) x[i] = fmaf(x[i] * (1.f / 16.f), bn2_s[i], bn2_b[i]);
+    float z = b2;
+    for (int o = 0; o < 32; ++o) {
+        float h = b1[o];
+        for (int i = 0; i < F; ++i) h = fmaf(w1[o * F + i], x[i], h);
+        h = fmaxf(fmaf(h, bn3_s[o], bn3_b[o]), 0.f);
+        z = fmaf(w2[o], h, z);
+    }
+    probs[ct.feat_off[chan] + local] = 1.f / (1.f + expf(-z));
+}
+
+cudaError_t launch_stem(const StemLaunch& L, const ChannelTable& ct, const float* feats, long long chunk_row0,
+                        int rows, cudaStream_t stream) {
+    const long long pixels = static_cast<long long>(rows) * (L.W + 2);
+    dim3 grid(static_cast<unsigned>((pixels + 255) / 256), L.n_jobs);
+    stem_kernel<<<grid, 256, 0, stream>>>(L, ct, feats, chunk_row0, rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_head(const HeadLaunch& L, const ChannelTable& ct, float* probs, long long chunk_row0, int nb,
+                        cudaStream_t stream) {
+    const int F = L.n_feat;
+    const size_t smem = sizeof(float) * (2 * F + 32 * F + 32 + 64 + 32 + 1);
+    head_kernel<<<(nb + 127) / 128, 128, smem, stream>>>(L, ct, probs, chunk_row0, nb);
+    return cudaGetLastError();
+}
+
+}  // namespace ld

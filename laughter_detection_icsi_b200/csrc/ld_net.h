@@ -1,0 +1,84 @@
+// Launch descriptions and launcher prototypes of the non-GEMM kernels.
+#pragma once
+#include <cstdint>
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "ld_types.h"
+
+namespace ld {
+
+constexpr int kMaxHeadFeat = 64;
+constexpr int kMaxHeadRows = 16;
+constexpr int kMaxStemJobs = 4;
+
+// Channels laid end to end in a sequence; all arrays live in device memory.
+struct ChannelTable {
+    const long long* seq_off;   // [n_chan] first sequence row of the channel
+    const long long* frames;    // [n_chan] T_c
+    const long long* feat_off;  // [n_chan] first row of the channel in the caller's feature/prob arrays
+    int n_chan;
+};
+
+struct StemJob {
+    __half* out;
+    long long kc_stride;
+    int row_shift;
+    int mask;
+};
+struct StemLaunch {
+    StemJob jobs[kMaxStemJobs];
+    const float* w;      // [64][9]
+    const float* scale;  // [64]
+    const float* shift;  // [64]
+    int n_jobs, W;
+};
+
+struct HeadRow {
+    const __half* plane;
+    long long kc_stride;
+    int row_shift;
+    int pad_;
+};
+struct HeadLaunch {
+    HeadRow rows[kMaxHeadRows];
+    const float* params;  // bn2 scale/shift, linear1, bn3 scale/shift, linear2 (see ld_net.cu)
+    int n_feat, C, groups, wp;
+};
+
+cudaError_t launch_stem(const StemLaunch& L, const ChannelTable& ct, const float* feats, long long chunk_row0,
+                        int rows, cudaStream_t stream);
+cudaError_t launch_head(const HeadLaunch& L, const ChannelTable& ct, float* probs, long long chunk_row0, int nb,
+                        cudaStream_t stream);
+
+// ld_gemm.cu
+cudaError_t launch_gemm_taps(const GemmLaunch* d_launch, const GemmLaunch& h, int m_tiles, int M, int num_sms,
+                             cudaStream_t stream);
+int gemm_pick_stages(int cin, int cout, int n_wtaps, int ext_alloc);
+
+// ld_fbank.cu
+struct FbankMel {           // sparse view of the (257, F) filterbank, built from the caller's matrix
+    const float* weights;   // packed nonzero runs, filter after filter
+    const int* lo;          // [F] first bin of filter k's run
+    const int* len;         // [F] run length
+    const int* off;         // [F] offset of the run inside weights
+    int n_filters;
+};
+cudaError_t launch_pcm_sum(const int16_t* pcm, long long n, unsigned long long* sum_biased, cudaStream_t stream);
+cudaError_t launch_fbank(const int16_t* pcm, long long n_samples, long long n_frames,
+                         const unsigned long long* sum_biased, int per_frame,
+                         const FbankMel& mel, const float* tables, float* feats, cudaStream_t stream);
+void fbank_host_tables(float* out /* kFbankTableFloats */);
+constexpr int kFbankTableFloats = 400 + 2 * 256 + 2 * 257;
+
+// ld_segment.cu
+cudaError_t launch_segment_runs(const void* probs, int is_f64, const ChannelTable& ct, long long total_frames,
+                                const double* thr_cmp_d, const double* thr_raw_d, int n_thr, int* starts, int* ends,
+                                int* chans, int* counts, int cap, int* block_counts, cudaStream_t stream);
+size_t segment_scratch_ints(long long total_frames, int n_thr);
+cudaError_t launch_filtfilt(const void* probs, int is_f64, long long n, const double* b, const double* a, double* out,
+                            double* scratch, cudaStream_t stream);
+size_t filtfilt_scratch_doubles(long long n);
+
+}  // namespace ld
