@@ -1,0 +1,238 @@
+"""Host-side handle on one GPU's ld_ctx: torch tensors in, torch tensors out, everything computed by
+the hand-written sm_100a kernels behind the C ABI (include/ld_b200.h).  PyTorch is used for device
+memory and streams only.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import LdError, LdTensor, check, f64_array, i64_array
+
+NUM_BINS = 257  # 512-point real FFT
+SAMPLE_RATE = 16000  # ICSI audio; lhotse FbankConfig default (train.py:65 in the reference)
+
+
+def lhotse_mel_matrix(num_filters=44, sampling_rate=SAMPLE_RATE, fft_length=512, low_freq=20.0, high_freq=-400.0):
+    """(257, num_filters) float32 filterbank of lhotse@f1b66b8 ``create_mel_scale`` (norm_filters=False):
+    HTK-style mel scale 1127*ln(1+f/700), centres linspace(mel(20), mel(7600), F+2), bin frequencies
+    ``linspace(0, sampling_rate, fft_length)`` (the pinned version's spacing), triangular weights.
+    Pure host-side setup data for K1 -- the kernel takes the matrix at run time."""
+    if high_freq <= 0:
+        high_freq = sampling_rate / 2 + high_freq
+    mel = lambda f: 1127.0 * np.log(1.0 + np.asarray(f, dtype=np.float64) / 700.0)
+    melfc = np.linspace(mel(low_freq), mel(high_freq), num_filters + 2)
+    mels = mel(np.linspace(0, sampling_rate, fft_length))
+    B = np.zeros((fft_length // 2 + 1, num_filters), dtype=np.float32)
+    for k in range(num_filters):
+        left, center, right = melfc[k], melfc[k + 1], melfc[k + 2]
+        for j in range(fft_length // 2):
+            m = mels[j]
+            if left < m < right:
+                B[j, k] = (m - left) / (center - left) if m <= center else (right - m) / (right - center)
+    return B
+
+
+def kaldi_mel_matrix(num_filters=44, sampling_rate=SAMPLE_RATE, fft_length=512, low_freq=20.0, high_freq=-400.0):
+    """(257, num_filters) float32 Kaldi/torchaudio ``get_mel_banks`` filterbank (no VTLN)."""
+    nyquist = 0.5 * sampling_rate
+    if high_freq <= 0:
+        high_freq += nyquist
+    mel = lambda f: 1127.0 * np.log(1.0 + np.asarray(f, dtype=np.float64) / 700.0)
+    fft_bin_width = sampling_rate / fft_length
+    mel_low, mel_high = mel(low_freq), mel(high_freq)
+    delta = (mel_high - mel_low) / (num_filters + 1)
+    B = np.zeros((fft_length // 2 + 1, num_filters), dtype=np.float32)
+    melj = mel(fft_bin_width * np.arange(fft_length // 2))
+    for k in range(num_filters):
+        left, center, right = mel_low + k * delta, mel_low + (k + 1) * delta, mel_low + (k + 2) * delta
+        up = (melj - left) / (center - left)
+        down = (right - melj) / (right - center)
+        B[: fft_length // 2, k] = np.maximum(0.0, np.minimum(up, down)).astype(np.float32)
+    return B
+
+
+class Engine:
+    """One ld_ctx on one CUDA device."""
+
+    def __init__(self, device=0, chunk_rows=0, fbank_preproc=_native.LD_PREPROC_UTTERANCE, filter_sizes=(64, 32, 16, 16),
+                 linear_layer_size=48):
+        self.lib = _native.load_library()
+        if not torch.cuda.is_available():
+            raise LdError("no CUDA device: the B200 kernels cannot run and there is no CPU fallback")
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.cfg = _native.default_config(chunk_rows=chunk_rows, fbank_preproc=fbank_preproc, filter_sizes=filter_sizes,
+                                          linear_layer_size=linear_layer_size)
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)  # make sure the primary context exists
+            h = ctypes.c_void_p()
+            check(self.lib.ld_create(self.device.index, ctypes.byref(self.cfg), ctypes.byref(h)))
+        self._h = h
+        self._mel_cache = {}
+        self.weights_loaded = False
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ld_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict):
+        """model.load_state_dict + eval(): fold BatchNorm, repack convs (segment_laughter.py:63-72)."""
+        keep, tensors = [], []
+        for name, t in state_dict.items():
+            if not torch.is_tensor(t) or not t.dtype.is_floating_point:
+                continue
+            a = np.ascontiguousarray(t.detach().cpu().float().numpy())
+            keep.append((name.encode(), a))
+        arr = (LdTensor * len(keep))()
+        for i, (n, a) in enumerate(keep):
+            arr[i].name = n
+            arr[i].data = a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+            arr[i].numel = a.size
+        check(self.lib.ld_resnet_load_weights(self._h, arr, len(keep)))
+        self.weights_loaded = True
+
+    # ------------------------------------------------------------------------------------------ K1
+    def mel_device(self, mel):
+        key = id(mel) if not isinstance(mel, str) else mel
+        if key not in self._mel_cache:
+            if isinstance(mel, str):
+                m = {"lhotse": lhotse_mel_matrix, "kaldi": kaldi_mel_matrix}[mel](self.cfg.num_filters)
+            else:
+                m = np.asarray(mel, dtype=np.float32)
+            if m.shape != (NUM_BINS, self.cfg.num_filters):
+                raise ValueError(f"mel matrix must be ({NUM_BINS}, {self.cfg.num_filters})")
+            self._mel_cache[key] = (torch.from_numpy(np.ascontiguousarray(m)).to(self.device), mel)
+        return self._mel_cache[key][0]
+
+    def fbank(self, pcm, chan_len=None, mel="lhotse"):
+        """pcm: int16 CUDA tensor (channels laid end to end); returns ((sum T, F) float32, [T_c])."""
+        if pcm.dtype != torch.int16 or not pcm.is_cuda:
+            raise ValueError("pcm must be an int16 CUDA tensor")
+        pcm = pcm.contiguous().reshape(-1)
+        chan_len = [pcm.numel()] if chan_len is None else [int(x) for x in chan_len]
+        if sum(chan_len) != pcm.numel():
+            raise ValueError("chan_len does not add up to the number of samples")
+        frames = [int(self.lib.ld_fbank_num_frames(n)) for n in chan_len]
+        feats = torch.empty((sum(frames), self.cfg.num_filters), dtype=torch.float32, device=self.device)
+        mel_d = self.mel_device(mel)
+        with torch.cuda.device(self.device):
+            check(self.lib.ld_fbank_i16(self._h, pcm.data_ptr(), i64_array(chan_len), len(chan_len), mel_d.data_ptr(),
+                                        feats.data_ptr(), None, self._stream()))
+        return feats, frames
+
+    # ------------------------------------------------------------------------------------------ K2 + K3
+    def infer_windows(self, feats, chan_frames=None):
+        """Probability of every frame's 100-frame window (InferenceDataset semantics). feats: (sum T, F) CUDA fp32."""
+        if feats.dtype != torch.float32 or not feats.is_cuda or feats.dim() != 2 or feats.shape[1] != self.cfg.num_filters:
+            raise ValueError("feats must be a float32 CUDA tensor of shape (T, num_filters)")
+        feats = feats.contiguous()
+        chan_frames = [feats.shape[0]] if chan_frames is None else [int(x) for x in chan_frames]
+        if sum(chan_frames) != feats.shape[0]:
+            raise ValueError("chan_frames does not add up to the number of feature rows")
+        probs = torch.empty(feats.shape[0], dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ld_resnet_infer_windows(self._h, feats.data_ptr(), i64_array(chan_frames), len(chan_frames),
+                                                   probs.data_ptr(), self._stream()))
+        return probs
+
+    def infer_pcm_host(self, pcm_host, chan_len, mel="lhotse"):
+        """End to end with HOST buffers (H2D of the PCM and D2H of the probabilities inside the call)."""
+        pcm_host = pcm_host.reshape(-1)
+        if pcm_host.dtype != torch.int16 or pcm_host.is_cuda:
+            raise ValueError("pcm_host must be an int16 host tensor")
+        chan_len = [int(x) for x in chan_len]
+        frames = [int(self.lib.ld_fbank_num_frames(n)) for n in chan_len]
+        probs = torch.empty(sum(frames), dtype=torch.float32, pin_memory=True)
+        m = self.mel_device(mel).cpu().contiguous()
+        with torch.cuda.device(self.device):
+            check(self.lib.ld_infer_pcm_host(self._h, pcm_host.data_ptr(), i64_array(chan_len), len(chan_len), m.data_ptr(),
+                                             probs.data_ptr(), self._stream()))
+        return probs, frames
+
+    # ------------------------------------------------------------------------------------------ K4 / K5
+    def segment_runs(self, probs, thr_cmp, thr_raw=None, chan_frames=None, cap=None):
+        """Maximal runs of clamp(p) > thr per threshold: list (per threshold) of (starts, ends, chans) int32 numpy."""
+        if not probs.is_cuda or probs.dtype not in (torch.float32, torch.float64):
+            raise ValueError("probs must be a float32/float64 CUDA tensor")
+        probs = probs.contiguous().reshape(-1)
+        chan_frames = [probs.numel()] if chan_frames is None else [int(x) for x in chan_frames]
+        thr_raw = thr_cmp if thr_raw is None else thr_raw
+        n_thr = len(thr_cmp)
+        cap = int(cap) if cap else max(1024, probs.numel() // 64)
+        while True:
+            starts = torch.empty((n_thr, cap), dtype=torch.int32, device=self.device)
+            ends = torch.empty_like(starts)
+            chans = torch.empty_like(starts)
+            counts = torch.zeros(n_thr, dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                check(self.lib.ld_segment_runs(self._h, probs.data_ptr(), int(probs.dtype == torch.float64),
+                                               i64_array(chan_frames), len(chan_frames), f64_array(thr_cmp), f64_array(thr_raw),
+                                               n_thr, starts.data_ptr(), ends.data_ptr(), chans.data_ptr(), counts.data_ptr(),
+                                               cap, self._stream()))
+            cnt = counts.cpu().numpy()
+            if cnt.max(initial=0) <= cap:
+                break
+            cap = int(cnt.max()) + 16
+        s, e, c = starts.cpu().numpy(), ends.cpu().numpy(), chans.cpu().numpy()
+        return [(s[k, :cnt[k]].copy(), e[k, :cnt[k]].copy(), c[k, :cnt[k]].copy()) for k in range(n_thr)]
+
+    def filter_min_length(self, starts, ends, fps, min_len):
+        """float64 frame->seconds and strict `end - start > min_len` (laugh_segmenter.py:23-24,108)."""
+        starts = np.ascontiguousarray(starts, dtype=np.int32)
+        ends = np.ascontiguousarray(ends, dtype=np.int32)
+        n = len(starts)
+        os_, oe = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
+        I32, F64 = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)
+        kept = self.lib.ld_filter_min_length(starts.ctypes.data_as(I32), ends.ctypes.data_as(I32), n, float(fps), float(min_len),
+                                             os_.ctypes.data_as(F64), oe.ctypes.data_as(F64))
+        return os_[:kept], oe[:kept]
+
+    def lowpass(self, probs, cutoff=0.01):
+        """filtfilt(butter(2, cutoff)) -> float64 CUDA tensor (laugh_segmenter.py:49-55)."""
+        probs = probs.contiguous().reshape(-1)
+        b, a = f64_array([0, 0, 0]), f64_array([0, 0, 0])
+        self.lib.ld_butter2_lowpass(float(cutoff), b, a)
+        out = torch.empty(probs.numel(), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ld_lowpass_filtfilt(self._h, probs.data_ptr(), int(probs.dtype == torch.float64), probs.numel(), b, a,
+                                               out.data_ptr(), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------------------------------ introspection
+    def read_plane(self, plane_id, rows, wp, C):
+        out = np.empty((rows, wp, C), dtype=np.float32)
+        check(self.lib.ld_debug_read_plane(self._h, plane_id, rows, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    @property
+    def macs_per_row(self):
+        return float(self.lib.ld_plan_macs_per_row(self._h))
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.ld_kernel_launches(self._h))
+
+
+_engines = {}
+
+
+def get_engine(device=0, **kw):
+    """Process-wide engine per device (one context per GPU per process)."""
+    idx = device if isinstance(device, int) else (torch.device(device).index or 0)
+    key = (idx, tuple(sorted(kw.items())))
+    if key not in _engines:
+        _engines[key] = Engine(idx, **kw)
+    return _engines[key]
