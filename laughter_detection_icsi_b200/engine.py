@@ -72,6 +72,7 @@ class Engine:
         self._h = h
         self._mel_cache = {}
         self.weights_loaded = False
+        self.weights_owner = None  # the nn.Module whose parameters are currently loaded (models.py)
 
     def close(self):
         if getattr(self, "_h", None):
