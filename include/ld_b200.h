@@ -137,6 +137,15 @@ LD_API int64_t ld_plan_json(const ld_config* cfg, char* buf, int64_t cap);
 LD_API int ld_debug_read_plane(ld_ctx* ctx, int32_t plane_id, int64_t rows, float* out_host);
 /* Executed multiply-accumulates per sequence row of the streaming plan, and kernel launches so far. */
 LD_API double ld_plan_macs_per_row(const ld_ctx* ctx);
+LD_API double ld_plan_gemm_macs_per_row(const ld_ctx* ctx);
+
+/* Device timing per kernel class, for roofline reporting.  While enabled every launch is bracketed by CUDA events
+ * recorded on the launch stream.  Classes: 0 conv GEMM (K2), 1 stem, 2 head, 3 fbank (K1), 4 segmenter/low-pass.
+ * ld_timing_read synchronises the recorded events and returns the accumulated milliseconds and launch counts
+ * (arrays of LD_TIMING_CLASSES); reset != 0 clears the accumulators. */
+#define LD_TIMING_CLASSES 5
+LD_API int ld_timing_enable(ld_ctx* ctx, int32_t enable);
+LD_API int ld_timing_read(ld_ctx* ctx, double* out_ms, int64_t* out_launches, int32_t reset);
 LD_API int64_t ld_kernel_launches(const ld_ctx* ctx);
 
 #ifdef __cplusplus

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libld_b200.so")
 
 LD_PREPROC_UTTERANCE = 0
 LD_PREPROC_FRAME = 1
+TIMING_CLASSES = ("conv_gemm", "stem", "head", "fbank", "segment")
 
 
 class LdError(RuntimeError):
@@ -58,7 +59,10 @@ SIGNATURES = {
     "ld_plan_json": (c_int64, [POINTER(LdConfig), c_char_p, c_int64]),
     "ld_debug_read_plane": (c_int, [c_void_p, c_int32, c_int64, c_void_p]),
     "ld_plan_macs_per_row": (c_double, [c_void_p]),
+    "ld_plan_gemm_macs_per_row": (c_double, [c_void_p]),
     "ld_kernel_launches": (c_int64, [c_void_p]),
+    "ld_timing_enable": (c_int, [c_void_p, c_int32]),
+    "ld_timing_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int32]),
 }
 
 _lib = None

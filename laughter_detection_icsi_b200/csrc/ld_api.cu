@@ -99,7 +99,33 @@ struct ld_ctx {
     DeviceBuf chan_table, seg_scratch, iir_scratch, thr_buf;
     DeviceBuf e2e_pcm, e2e_feats, e2e_probs, e2e_mel;
     long long launches = 0;
+    // optional per-class device timing
+    bool timing = false;
+    struct TimedSpan { int cls; cudaEvent_t a, b; };
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> event_pool;
+    double class_ms[LD_TIMING_CLASSES] = {0, 0, 0, 0, 0};
+    long long class_launches[LD_TIMING_CLASSES] = {0, 0, 0, 0, 0};
 };
+
+namespace {
+// Brackets one (or a few) launches of a kernel class with events on the launch stream while timing is enabled.
+struct Timed {
+    ld_ctx* ctx; cudaStream_t s; int cls; int n; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(ld_ctx* c) {
+        if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr; cudaEventCreate(&e); return e;
+    }
+    Timed(ld_ctx* c, cudaStream_t st, int k, int launches = 1) : ctx(c), s(st), cls(k), n(launches) {
+        ctx->launches += n;
+        ctx->class_launches[cls] += n;
+        if (ctx->timing) { a = get(ctx); b = get(ctx); cudaEventRecord(a, s); }
+    }
+    ~Timed() {
+        if (a) { cudaEventRecord(b, s); ctx->spans.push_back({cls, a, b}); }
+    }
+};
+}  // namespace
 
 namespace {
 
@@ -389,6 +415,8 @@ void ld_destroy(ld_ctx* ctx) {
     if (ctx->fbank_tables) cudaFree(ctx->fbank_tables);
     if (ctx->pcm_sum) cudaFree(ctx->pcm_sum);
     ctx->mel_sparse.release(); ctx->chan_table.release(); ctx->seg_scratch.release(); ctx->iir_scratch.release();
+    for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     ctx->thr_buf.release(); ctx->e2e_pcm.release(); ctx->e2e_feats.release(); ctx->e2e_probs.release(); ctx->e2e_mel.release();
     delete ctx;
 }
@@ -472,16 +500,14 @@ int ld_resnet_infer_windows(ld_ctx* ctx, const float* feats_d, const int64_t* ch
     for (long long row0 = 0; row0 < seq_total; row0 += ctx->chunk_rows) {
         const int nb = static_cast<int>(std::min<long long>(ctx->chunk_rows, seq_total - row0));
         const int rows = nb + H;
-        LD_CUDA(ld::launch_stem(ctx->stem, ct, feats_d, row0, rows, stream));
-        ++ctx->launches;
+        { Timed t(ctx, stream, 1); LD_CUDA(ld::launch_stem(ctx->stem, ct, feats_d, row0, rows, stream)); }
         for (auto& cd : ctx->convs) {
             const int M = rows * cd.wp;
             const int m_tiles = (M + ld::kTileM - 1) / ld::kTileM;
+            Timed t(ctx, stream, 0);
             LD_CUDA(ld::launch_gemm_taps(cd.d, cd.h, m_tiles, M, ctx->num_sms, stream));
-            ++ctx->launches;
         }
-        LD_CUDA(ld::launch_head(ctx->head, ct, probs_d, row0, nb, stream));
-        ++ctx->launches;
+        { Timed t(ctx, stream, 2); LD_CUDA(ld::launch_head(ctx->head, ct, probs_d, row0, nb, stream)); }
     }
     return LD_OK;
 }
@@ -531,12 +557,9 @@ int ld_fbank_i16(ld_ctx* ctx, const int16_t* pcm_d, const int64_t* chan_len, int
         if (L < 200) return fail(LD_ERR_UNSUPPORTED, "recordings shorter than 200 samples are not supported");
         const long long T = (L + 80) / 160;
         unsigned long long* sum = ctx->pcm_sum + (c & 1023);
-        if (!per_frame) {
-            LD_CUDA(ld::launch_pcm_sum(pcm_d + s_off, L, sum, stream));
-            ++ctx->launches;
-        }
+        Timed t(ctx, stream, 3, per_frame ? 1 : 2);
+        if (!per_frame) LD_CUDA(ld::launch_pcm_sum(pcm_d + s_off, L, sum, stream));
         LD_CUDA(ld::launch_fbank(pcm_d + s_off, L, T, sum, per_frame, ctx->mel, ctx->fbank_tables, feats_d + f_off * F, stream));
-        ++ctx->launches;
         if (frames_out) frames_out[c] = T;
         s_off += L; f_off += T;
     }
@@ -561,9 +584,9 @@ int ld_segment_runs(ld_ctx* ctx, const void* probs_d, int32_t prob_is_f64, const
     LD_CUDA(cudaMemcpyAsync(thr_d + n_thr, thr_raw, sizeof(double) * n_thr, cudaMemcpyHostToDevice, stream));
     LD_CUDA(cudaStreamSynchronize(stream));
     if (int r = ctx->seg_scratch.ensure(ld::segment_scratch_ints(total, n_thr) * sizeof(int))) return r;
+    Timed t(ctx, stream, 4, 3);
     LD_CUDA(ld::launch_segment_runs(probs_d, prob_is_f64, ct, total, thr_d, thr_d + n_thr, n_thr, starts_d, ends_d, chan_d,
                                     counts_d, cap, static_cast<int*>(ctx->seg_scratch.p), stream));
-    ctx->launches += 3;
     return LD_OK;
 }
 
@@ -601,8 +624,8 @@ int ld_lowpass_filtfilt(ld_ctx* ctx, const void* probs_d, int32_t prob_is_f64, i
     LD_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     if (int r = ctx->iir_scratch.ensure(ld::filtfilt_scratch_doubles(n) * sizeof(double))) return r;
+    Timed t(ctx, stream, 4, 6);
     LD_CUDA(ld::launch_filtfilt(probs_d, prob_is_f64, n, b, a, out_d, static_cast<double*>(ctx->iir_scratch.p), stream));
-    ctx->launches += 6;
     return LD_OK;
 }
 
@@ -654,6 +677,33 @@ int ld_debug_read_plane(ld_ctx* ctx, int32_t plane_id, int64_t rows, float* out_
 }
 
 double ld_plan_macs_per_row(const ld_ctx* ctx) { return ctx ? ctx->plan.macs_per_row : 0.0; }
+double ld_plan_gemm_macs_per_row(const ld_ctx* ctx) { return ctx ? ctx->plan.gemm_macs_per_row : 0.0; }
+
+int ld_timing_enable(ld_ctx* ctx, int32_t enable) {
+    if (!ctx) return fail(LD_ERR_INVALID, "ctx is null");
+    ctx->timing = enable != 0;
+    return LD_OK;
+}
+
+int ld_timing_read(ld_ctx* ctx, double* out_ms, int64_t* out_launches, int32_t reset) {
+    if (!ctx) return fail(LD_ERR_INVALID, "ctx is null");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    for (auto& sp : ctx->spans) {
+        LD_CUDA(cudaEventSynchronize(sp.b));
+        float ms = 0.f;
+        LD_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        ctx->class_ms[sp.cls] += ms;
+        ctx->event_pool.push_back(sp.a);
+        ctx->event_pool.push_back(sp.b);
+    }
+    ctx->spans.clear();
+    for (int i = 0; i < LD_TIMING_CLASSES; ++i) {
+        if (out_ms) out_ms[i] = ctx->class_ms[i];
+        if (out_launches) out_launches[i] = ctx->class_launches[i];
+        if (reset) { ctx->class_ms[i] = 0; ctx->class_launches[i] = 0; }
+    }
+    return LD_OK;
+}
 int64_t ld_kernel_launches(const ld_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 }  // extern "C"

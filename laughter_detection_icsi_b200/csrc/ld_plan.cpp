@@ -264,8 +264,11 @@ Plan build_stream_plan(const NetConfig& cfg) {
             set_out(job, out.interior);
             L.jobs.push_back(job);
         }
-        for (auto& job : L.jobs)
-            plan.macs_per_row += static_cast<double>(job.taps.size()) * L.cin * L.cout * L.wp;
+        for (auto& job : L.jobs) {
+            const double m = static_cast<double>(job.taps.size()) * L.cin * L.cout * L.wp;
+            plan.macs_per_row += m;
+            plan.gemm_macs_per_row += m;
+        }
         // split launches that exceed the per-launch job table
         for (size_t o = 0; o < L.jobs.size(); o += kMaxJobs) {
             ConvLaunchSpec part = L;

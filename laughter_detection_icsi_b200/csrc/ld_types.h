@@ -105,7 +105,8 @@ struct Plan {
     std::vector<ConvLaunchSpec> convs;
     std::vector<HeadRowSpec> head_rows;  // the 12 local rows AvgPool2d(4) consumes
     int head_wp = 0, head_C = 0, head_pool_w = 0, head_pool_groups = 0;
-    double macs_per_row = 0;  // executed MACs per sequence row (all planes), for roofline accounting
+    double macs_per_row = 0;       // executed MACs per sequence row (all planes), for roofline accounting
+    double gemm_macs_per_row = 0;  // the tensor-core share of it (everything but the fp32 stem)
 };
 
 // ResNetBigger topology needed by the planner (models.py:181-244 in the reference).

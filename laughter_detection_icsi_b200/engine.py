@@ -187,7 +187,9 @@ class Engine:
             if cnt.max(initial=0) <= cap:
                 break
             cap = int(cnt.max()) + 16
-        s, e, c = starts.cpu().numpy(), ends.cpu().numpy(), chans.cpu().numpy()
+        m = int(cnt.max(initial=0))
+        s, e, c = (t[:, :m].contiguous().cpu().numpy() for t in (starts, ends, chans))
+        self.last_d2h_bytes = 4 * n_thr + 3 * 4 * n_thr * m
         return [(s[k, :cnt[k]].copy(), e[k, :cnt[k]].copy(), c[k, :cnt[k]].copy()) for k in range(n_thr)]
 
     def filter_min_length(self, starts, ends, fps, min_len):
@@ -221,6 +223,20 @@ class Engine:
     @property
     def macs_per_row(self):
         return float(self.lib.ld_plan_macs_per_row(self._h))
+
+    @property
+    def gemm_macs_per_row(self):
+        return float(self.lib.ld_plan_gemm_macs_per_row(self._h))
+
+    def timing_enable(self, enable=True):
+        check(self.lib.ld_timing_enable(self._h, int(bool(enable))))
+
+    def timing_read(self, reset=True):
+        """{class: (milliseconds, launches)} accumulated since the last reset (synchronises the recorded events)."""
+        n = len(_native.TIMING_CLASSES)
+        ms, cnt = (ctypes.c_double * n)(), (ctypes.c_int64 * n)()
+        check(self.lib.ld_timing_read(self._h, ms, cnt, int(bool(reset))))
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(_native.TIMING_CLASSES)}
 
     @property
     def kernel_launches(self):

@@ -1,0 +1,72 @@
+"""Batch inference over many channels: the whole hot path of segment_laughter.load_and_pred
+(reference segment_laughter.py:79-122) for a list of channels at once -- PCM -> log-mel (K1) -> per-frame
+ResNetBigger probabilities (K2+K3) -> threshold runs (K4) -> float64 min-length filter -- with one H2D copy
+of the PCM and one D2H copy of the run lists.  This is the call `bench.py` times end to end and the unit
+that is sharded across GPUs (one meeting's channels per rank, no collective in the loop).
+"""
+import numpy as np
+import torch
+
+from . import engine as _engine
+from . import laugh_segmenter
+
+
+class LaughterPipeline:
+    def __init__(self, state_dict, device=0, thresholds=(0.5,), min_lengths=(0.2,), mel="lhotse", **engine_kw):
+        self.engine = _engine.get_engine(device, **engine_kw)
+        self.engine.load_state_dict(state_dict)
+        self.engine.weights_owner = self
+        self.thresholds = [float(t) for t in thresholds]
+        self.min_lengths = [float(m) for m in min_lengths]
+        self.mel = mel
+        self._cap = None
+
+    # --- device-resident stages ------------------------------------------------------------------------
+    def probabilities(self, pcm_dev, chan_len):
+        """int16 CUDA PCM (channels end to end) -> (float32 CUDA probs, frames per channel)."""
+        feats, frames = self.engine.fbank(pcm_dev, chan_len, mel=self.mel)
+        return self.engine.infer_windows(feats, frames), frames
+
+    def runs(self, probs_dev, frames):
+        """Per threshold: (starts, ends, channel) int32 numpy arrays of all maximal runs above the threshold."""
+        thr_cmp = laugh_segmenter.comparison_thresholds(self.thresholds, probs_dev.dtype == torch.float32)
+        out = self.engine.segment_runs(probs_dev, thr_cmp, self.thresholds, frames, cap=self._cap)
+        self._cap = max(self._cap or 0, max(len(s) for s, _, _ in out) + 1024)
+        return out
+
+    def step_device(self, pcm_dev, chan_len):
+        """One pass of the hot path with inputs already in HBM; results stay on the device except the run lists."""
+        probs, frames = self.probabilities(pcm_dev, chan_len)
+        return self.runs(probs, frames), frames
+
+    # --- host in, host out ----------------------------------------------------------------------------
+    def instances(self, runs, frames, durations_s):
+        """runs -> per channel {(thr, min_len): [(start_s, end_s)]}, fps = frames / duration as in the reference."""
+        out = [dict() for _ in frames]
+        for (starts, ends, chans), thr in zip(runs, self.thresholds):
+            order = np.argsort(chans, kind="stable")
+            starts, ends, chans = starts[order], ends[order], chans[order]
+            bounds = np.searchsorted(chans, np.arange(len(frames) + 1))
+            for c in range(len(frames)):
+                s, e = starts[bounds[c]:bounds[c + 1]], ends[bounds[c]:bounds[c + 1]]
+                fps = frames[c] / float(durations_s[c])
+                for ml in self.min_lengths:
+                    a, b = self.engine.filter_min_length(s, e, fps, ml)
+                    out[c][(thr, ml)] = list(zip(a.tolist(), b.tolist()))
+        return out
+
+    def __call__(self, pcm_host, chan_len, durations_s=None):
+        """pcm_host: int16 host tensor (pinned for full copy bandwidth). Returns (per-channel instance dicts, frames)."""
+        pcm_dev = pcm_host.to(self.engine.device, non_blocking=True)
+        runs, frames = self.step_device(pcm_dev, chan_len)
+        if durations_s is None:
+            durations_s = [n / float(_engine.SAMPLE_RATE) for n in chan_len]
+        return self.instances(runs, frames, durations_s), frames
+
+    @staticmethod
+    def h2d_bytes(chan_len):
+        return 2 * int(sum(chan_len))
+
+    def d2h_bytes(self):
+        """Bytes the last `runs` call copied back (counts + the used part of the start/end/channel lists)."""
+        return int(self.engine.last_d2h_bytes)

@@ -25,14 +25,7 @@ import laugh_segmenter as ref_seg  # noqa: E402  (reference)
 import models as ref_models  # noqa: E402  (reference)
 
 from oracle import resnet_oracle  # noqa: E402
-
-
-def golden_inputs_resnet(seed=5, n=6):
-    rng = np.random.default_rng(seed)
-    x = rng.normal(-4.0, 3.0, (n, 1, 100, 44)).astype(np.float32)
-    x[1, :, 60:] = 0.0   # a tail window: zero rows, as InferenceDataset pads
-    x[2, :, 1:] = 0.0
-    return x
+from tests.golden.make_golden_inputs import expand_probs, golden_inputs_resnet  # noqa: E402
 
 
 def make_resnet():
@@ -50,19 +43,6 @@ def make_resnet():
     with open(os.path.join(HERE, "resnet_state_dict_keys.json"), "w") as f:
         json.dump({k: list(v.shape) for k, v in model.state_dict().items()}, f, indent=0)
     print("resnet golden:", y.reshape(-1))
-
-
-def expand_probs(case):
-    """Cases either store their probabilities or a tiny generator spec (keeps the fixture small)."""
-    if "probs" in case:
-        return case["probs"]
-    g = case["gen"]
-    if g["kind"] == "minlen_edge":
-        v = [0.1] * 260
-        for i in range(g["start"], g["start"] + 21):
-            v[i] = 0.9
-        return v
-    raise ValueError(g)
 
 
 def seg_cases():

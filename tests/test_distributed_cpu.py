@@ -1,0 +1,48 @@
+"""World-size-2 gloo test of the host-side sharding / gather logic used for multi-GPU inference."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from laughter_detection_icsi_b200 import distributed as ldd
+
+
+def test_shard_units_balanced_and_complete():
+    durations = [3600, 1800, 3500, 10, 1800, 3600, 900]
+    shards = ldd.shard_units(durations, 3)
+    assert sorted(i for s in shards for i in s) == list(range(len(durations)))
+    loads = [sum(durations[i] for i in s) for s in shards]
+    assert max(loads) - min(loads) <= max(durations)
+    assert ldd.shard_units(durations, 3) == shards  # deterministic
+    assert ldd.shard_units([1, 1], 4) == [[0], [1], [], []]
+
+
+def _worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    durations = [50.0, 10.0, 30.0, 20.0, 40.0]
+    mine = ldd.shard_units(durations, world)[rank]
+    # stand-in for the per-channel result of the GPU pipeline: {setting: [(start, end)]}
+    local = [{(0.5, 0.2): [(float(u), float(u) + durations[u] / 100.0)], "rank": rank} for u in mine]
+    merged = ldd.gather_results(local, mine, len(durations), dst=0)
+    t = torch.tensor([float(len(mine))])
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        assert t.item() == len(durations)
+        assert [list(m[(0.5, 0.2)][0])[0] for m in merged] == [0.0, 1.0, 2.0, 3.0, 4.0]
+        torch.save({"ranks": [m["rank"] for m in merged]}, out_path)
+    else:
+        assert merged is None
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_over_gloo(tmp_path):
+    out = str(tmp_path / "merged.pt")
+    mp.spawn(_worker, args=(2, 29531 + os.getpid() % 500, out), nprocs=2, join=True)
+    ranks = torch.load(out)["ranks"]
+    assert sorted(set(ranks)) == [0, 1] and len(ranks) == 5
+
+
+def test_single_process_gather_is_identity():
+    assert ldd.gather_results(["a", "b"], [1, 0], 2) == ["b", "a"]
