@@ -183,6 +183,7 @@ def run_b200(args):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     eng.timing_enable(False)
+    conv_ms = eng.timing_read_convs(reset=True)
     timing = eng.timing_read(reset=True)
     launches = eng.kernel_launches - launches0
     windows_per_step = sum(frames)
@@ -242,6 +243,7 @@ def run_b200(args):
                 "executed_tflops": exec_tf, "executed_frac": exec_tf / peaks["tflops"] if exec_tf else None,
                 "kernel_ms_per_step": gemm_ms / args.steps, "kernel_launches_per_step": gemm_launches / args.steps,
                 "kernel_share_of_step": gemm_ms / ms if ms else None,
+                "per_conv_ms_per_step": {name: round(v / args.steps, 3) for name, v in conv_ms},
                 "peak_source": peaks["source"], "traffic": prof.get("gemm_dram_bytes_per_launch"),
                 "fbank": {"bound": "hbm", "unit": "GB/s", "achieved": 496.0 * windows_per_step * args.steps / (fbank_ms * 1e-3) / 1e9
                           if fbank_ms else None, "peak": peaks["hbm_gbs"], "ms_per_step": fbank_ms / args.steps,

@@ -147,6 +147,8 @@ LD_API double ld_plan_gemm_macs_per_row(const ld_ctx* ctx);
 LD_API int ld_timing_enable(ld_ctx* ctx, int32_t enable);
 LD_API int ld_timing_read(ld_ctx* ctx, double* out_ms, int64_t* out_launches, int32_t reset);
 LD_API int64_t ld_kernel_launches(const ld_ctx* ctx);
+/* Accumulated milliseconds of each conv launch of the plan (order of ld_plan_json's "convs"); returns their number. */
+LD_API int32_t ld_timing_read_convs(ld_ctx* ctx, double* out_ms, int32_t cap, int32_t reset);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,7 @@ SIGNATURES = {
     "ld_kernel_launches": (c_int64, [c_void_p]),
     "ld_timing_enable": (c_int, [c_void_p, c_int32]),
     "ld_timing_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int32]),
+    "ld_timing_read_convs": (c_int32, [c_void_p, POINTER(c_double), c_int32, c_int32]),
 }
 
 _lib = None

@@ -101,28 +101,30 @@ struct ld_ctx {
     long long launches = 0;
     // optional per-class device timing
     bool timing = false;
-    struct TimedSpan { int cls; cudaEvent_t a, b; };
+    struct TimedSpan { int cls; int sub; cudaEvent_t a, b; };
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> event_pool;
     double class_ms[LD_TIMING_CLASSES] = {0, 0, 0, 0, 0};
     long long class_launches[LD_TIMING_CLASSES] = {0, 0, 0, 0, 0};
+    std::vector<double> conv_ms;  // per conv launch of the plan, accumulated while timing is enabled
 };
 
 namespace {
 // Brackets one (or a few) launches of a kernel class with events on the launch stream while timing is enabled.
 struct Timed {
-    ld_ctx* ctx; cudaStream_t s; int cls; int n; cudaEvent_t a = nullptr, b = nullptr;
+    ld_ctx* ctx; cudaStream_t s; int cls; int n; int sub; cudaEvent_t a = nullptr, b = nullptr;
     static cudaEvent_t get(ld_ctx* c) {
         if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
         cudaEvent_t e = nullptr; cudaEventCreate(&e); return e;
     }
-    Timed(ld_ctx* c, cudaStream_t st, int k, int launches = 1) : ctx(c), s(st), cls(k), n(launches) {
+    Timed(ld_ctx* c, cudaStream_t st, int k, int launches = 1, int sub_index = -1)
+        : ctx(c), s(st), cls(k), n(launches), sub(sub_index) {
         ctx->launches += n;
         ctx->class_launches[cls] += n;
         if (ctx->timing) { a = get(ctx); b = get(ctx); cudaEventRecord(a, s); }
     }
     ~Timed() {
-        if (a) { cudaEventRecord(b, s); ctx->spans.push_back({cls, a, b}); }
+        if (a) { cudaEventRecord(b, s); ctx->spans.push_back({cls, sub, a, b}); }
     }
 };
 }  // namespace
@@ -344,6 +346,9 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
                 job.taps[t].group = static_cast<int16_t>(g);
                 job.taps[t].off = static_cast<int16_t>(taps[t].shift - g_min);
                 job.taps[t].wtap = static_cast<int16_t>(taps[t].wtap);
+                job.tap_a16[t] = static_cast<uint16_t>(taps[t].shift - g_min);
+                job.tap_b16[t] = static_cast<uint16_t>(taps[t].wtap * (cs.cin / 8) * cs.cout);
+                job.group_taps[g] = static_cast<uint8_t>(job.group_taps[g] + 1);
             }
             job.n_groups = g + 1;
             job.n_taps = static_cast<int>(taps.size());
@@ -501,10 +506,11 @@ int ld_resnet_infer_windows(ld_ctx* ctx, const float* feats_d, const int64_t* ch
         const int nb = static_cast<int>(std::min<long long>(ctx->chunk_rows, seq_total - row0));
         const int rows = nb + H;
         { Timed t(ctx, stream, 1); LD_CUDA(ld::launch_stem(ctx->stem, ct, feats_d, row0, rows, stream)); }
-        for (auto& cd : ctx->convs) {
+        for (size_t ci = 0; ci < ctx->convs.size(); ++ci) {
+            auto& cd = ctx->convs[ci];
             const int M = rows * cd.wp;
             const int m_tiles = (M + ld::kTileM - 1) / ld::kTileM;
-            Timed t(ctx, stream, 0);
+            Timed t(ctx, stream, 0, 1, static_cast<int>(ci));
             LD_CUDA(ld::launch_gemm_taps(cd.d, cd.h, m_tiles, M, ctx->num_sms, stream));
         }
         { Timed t(ctx, stream, 2); LD_CUDA(ld::launch_head(ctx->head, ct, probs_d, row0, nb, stream)); }
@@ -693,6 +699,10 @@ int ld_timing_read(ld_ctx* ctx, double* out_ms, int64_t* out_launches, int32_t r
         float ms = 0.f;
         LD_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
         ctx->class_ms[sp.cls] += ms;
+        if (sp.sub >= 0) {
+            if (ctx->conv_ms.size() <= static_cast<size_t>(sp.sub)) ctx->conv_ms.resize(sp.sub + 1, 0.0);
+            ctx->conv_ms[sp.sub] += ms;
+        }
         ctx->event_pool.push_back(sp.a);
         ctx->event_pool.push_back(sp.b);
     }
@@ -705,5 +715,14 @@ int ld_timing_read(ld_ctx* ctx, double* out_ms, int64_t* out_launches, int32_t r
     return LD_OK;
 }
 int64_t ld_kernel_launches(const ld_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t ld_timing_read_convs(ld_ctx* ctx, double* out_ms, int32_t cap, int32_t reset) {
+    if (!ctx) return fail(LD_ERR_INVALID, "ctx is null");
+    if (int r = ld_timing_read(ctx, nullptr, nullptr, 0)) return r;  // drains the recorded spans
+    const int32_t n = static_cast<int32_t>(ctx->convs.size());
+    for (int32_t i = 0; i < n && i < cap; ++i) out_ms[i] = i < static_cast<int32_t>(ctx->conv_ms.size()) ? ctx->conv_ms[i] : 0.0;
+    if (reset) ctx->conv_ms.assign(ctx->conv_ms.size(), 0.0);
+    return n;
+}
 
 }  // extern "C"

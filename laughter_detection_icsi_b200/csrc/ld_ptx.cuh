@@ -116,7 +116,47 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 
+// TMEM -> registers: 32 lanes x 32-bit, 32 consecutive columns per thread.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+// N consecutive accumulator columns (N a multiple of 16); the caller issues tmem_wait_ld() once afterwards.
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[N]) {
+    static_assert(N % 16 == 0 && N >= 16 && N <= 128, "accumulator width");
+#pragma unroll
+    for (int c = 0; c + 32 <= N; c += 32) tmem_ld32(taddr + c, v + c);
+    if (N % 32 != 0) {
+        uint32_t(&t)[16] = *reinterpret_cast<uint32_t(*)[16]>(v + (N - 16));
+        tmem_ld16(taddr + (N - 16), t);
+    }
+}
+
+// 16-byte read-only global load that does not allocate in L1 (streamed once per tile).
+__device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
 // ---------------------------------------------------------------- descriptors
+__device__ __forceinline__ uint64_t umma_pack_desc(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
 // Shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleaved") canonical layout:
 // in 16-byte units ((8,n),2):((1,SBO),LBO) -- a core matrix is 8 rows x 16 B stored contiguously
 // (rows 16 B apart); SBO = byte distance between 8-row groups, LBO = byte distance between the two

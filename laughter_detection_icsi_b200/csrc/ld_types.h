@@ -42,6 +42,10 @@ struct GemmTap {
 struct GemmJob {
     GemmGroup groups[kMaxGroups];
     GemmTap taps[kMaxTaps];
+    // MMA-issue view of the taps, in smem-descriptor units (16 bytes), ordered by group:
+    uint16_t tap_a16[kMaxTaps];      // pixel offset of the tap inside its group's load (1 pixel = 16 B per chunk)
+    uint16_t tap_b16[kMaxTaps + 2];  // offset of the tap's weight slab inside the weight block
+    uint8_t group_taps[kMaxGroups + 2];  // taps per group
     int32_t n_groups, n_taps;
     __half* out0;  // PLAIN: the plane; COLSPLIT: even-column plane
     __half* out1;  // COLSPLIT: odd-column plane

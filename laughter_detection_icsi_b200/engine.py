@@ -238,6 +238,15 @@ class Engine:
         check(self.lib.ld_timing_read(self._h, ms, cnt, int(bool(reset))))
         return {name: (ms[i], cnt[i]) for i, name in enumerate(_native.TIMING_CLASSES)}
 
+    def timing_read_convs(self, reset=True):
+        """[(conv name, accumulated ms)] per conv launch of the plan."""
+        ms = (ctypes.c_double * 64)()
+        n = self.lib.ld_timing_read_convs(self._h, ms, 64, int(bool(reset)))
+        if n < 0:
+            check(n)
+        names = [c["conv"] for c in _native.plan_json(self.cfg)["convs"]]
+        return [(names[i], ms[i]) for i in range(n)]
+
     @property
     def kernel_launches(self):
         return int(self.lib.ld_kernel_launches(self._h))
