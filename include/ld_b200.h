@@ -149,6 +149,10 @@ LD_API int ld_timing_read(ld_ctx* ctx, double* out_ms, int64_t* out_launches, in
 LD_API int64_t ld_kernel_launches(const ld_ctx* ctx);
 /* Accumulated milliseconds of each conv launch of the plan (order of ld_plan_json's "convs"); returns their number. */
 LD_API int32_t ld_timing_read_convs(ld_ctx* ctx, double* out_ms, int32_t cap, int32_t reset);
+/* Debug (context created with LD_GEMM_PROF=1 in the environment): 8 cycle counters per conv launch, summed over CTAs:
+ * producer wait, MMA wait-operands, MMA wait-accumulator, MMA issue, epilogue wait, epilogue work, CTA lifetime, tiles.
+ * Returns the number of conv launches (0 when the counters are off). */
+LD_API int32_t ld_debug_gemm_counters(ld_ctx* ctx, uint64_t* out, int32_t cap_convs, int32_t reset);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,7 @@ SIGNATURES = {
     "ld_timing_enable": (c_int, [c_void_p, c_int32]),
     "ld_timing_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int32]),
     "ld_timing_read_convs": (c_int32, [c_void_p, POINTER(c_double), c_int32, c_int32]),
+    "ld_debug_gemm_counters": (c_int32, [c_void_p, POINTER(ctypes.c_uint64), c_int32, c_int32]),
 }
 
 _lib = None

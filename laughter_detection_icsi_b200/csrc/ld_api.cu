@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -41,15 +42,14 @@ struct PlaneDev {
 
 struct ConvWeights {
     __half* w = nullptr;
-    float* scale = nullptr;
     float* shift = nullptr;
     int cin = 0, cout = 0, ksize = 0;
+    bool has_res = false;  // the launches of this conv add a residual: one extra identity weight slab
     std::string conv, bn;
 };
 
 struct ConvLaunchDev {
-    ld::GemmLaunch h;
-    ld::GemmLaunch* d = nullptr;
+    ld::GemmLaunch h;   // passed to the kernel by value (__grid_constant__)
     int wp = 0;
 };
 
@@ -80,6 +80,8 @@ struct ld_ctx {
     int rows_alloc = 0;   // rows per plane (chunk_rows + H)
     uint8_t* workspace = nullptr;
     size_t workspace_bytes = 0;
+    CUtensorMap* tmaps = nullptr;  // device array, one TMA descriptor per plane
+    unsigned long long* gemm_prof = nullptr;  // LD_GEMM_PROF=1: 8 cycle counters per conv launch
     std::vector<PlaneDev> planes;
     std::map<std::string, ConvWeights> weights;
     std::vector<ConvLaunchDev> convs;
@@ -277,7 +279,7 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         PlaneDev& pd = ctx->planes[i];
         const long long guard = static_cast<long long>(ld::kGuardRows) * ps.wp + 256;
         pd.C = ps.C; pd.wp = ps.wp;
-        pd.pixels_alloc = static_cast<long long>(ctx->rows_alloc) * ps.wp + 2 * guard;
+        pd.pixels_alloc = (static_cast<long long>(ctx->rows_alloc) * ps.wp + 2 * guard + 7) & ~7ll;  // chunk stride stays 128 B aligned
         pd.kc_stride = pd.pixels_alloc * 8;
         offs[i] = total;
         total += static_cast<size_t>(pd.pixels_alloc) * 16 * (ps.C / 8);
@@ -291,14 +293,45 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         ctx->planes[i].base = reinterpret_cast<__half*>(ctx->workspace + offs[i]) + guard * 8;
     }
 
+    // ---- one TMA descriptor per plane: (8 halfs, pixels incl. guards, C/8 chunks), box (8, kBoxPixels, C/8) --------
+    {
+        typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                          CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        LD_CUDA_C(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (fn == nullptr || qres != cudaDriverEntryPointSuccess)
+            return cleanup_fail(fail(LD_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver"));
+        std::vector<CUtensorMap> maps(plan.planes.size());
+        for (size_t i = 0; i < plan.planes.size(); ++i) {
+            const PlaneDev& pd = ctx->planes[i];
+            const cuuint64_t dims[3] = {8, static_cast<cuuint64_t>(pd.pixels_alloc), static_cast<cuuint64_t>(pd.C / 8)};
+            const cuuint64_t strides[2] = {16, static_cast<cuuint64_t>(pd.pixels_alloc) * 16};
+            const cuuint32_t box[3] = {8, static_cast<cuuint32_t>(ld::kBoxPixels), static_cast<cuuint32_t>(pd.C / 8)};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(
+                &maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ctx->workspace + offs[i], dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS)
+                return cleanup_fail(fail(LD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r))));
+        }
+        LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->tmaps), maps.size() * sizeof(CUtensorMap)));
+        LD_CUDA_C(cudaMemcpy(ctx->tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    }
+
     // ---- weights (allocated now so that launch tables can point at them; filled by load_weights) -----
     for (const auto& cs : plan.convs) {
         if (ctx->weights.count(cs.conv)) continue;
         ConvWeights w;
         w.cin = cs.cin; w.cout = cs.cout; w.ksize = cs.ksize; w.conv = cs.conv; w.bn = cs.bn;
-        const size_t n = static_cast<size_t>(cs.ksize) * cs.ksize * cs.cin * cs.cout;
+        for (const auto& other : plan.convs)
+            if (other.conv == cs.conv)
+                for (const auto& js : other.jobs) w.has_res = w.has_res || js.res_plane >= 0;
+        if (w.has_res && cs.cin != cs.cout) return cleanup_fail(fail(LD_ERR_INVALID, "residual conv with cin != cout: " + cs.conv));
+        const size_t n = (static_cast<size_t>(cs.ksize) * cs.ksize + (w.has_res ? 1 : 0)) * cs.cin * cs.cout;
         LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&w.w), n * sizeof(__half)));
-        LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&w.scale), cs.cout * sizeof(float)));
         LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&w.shift), cs.cout * sizeof(float)));
         ctx->weights[cs.conv] = w;
     }
@@ -309,6 +342,17 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
     LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->head_params), ctx->head_param_count * sizeof(float)));
 
     // ---- launch tables -----------------------------------------------------------------------------------
+    // tuning knobs (environment, read once per context): operand loader, load-group span, smem ring depth, counters
+    auto env_int = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
+    const int loader = env_int("LD_GEMM_LOADER", 0);
+    const int group_span = loader == 1 ? std::min(env_int("LD_GEMM_SPAN", 2), ld::kBoxPixels - ld::kTileM) : env_int("LD_GEMM_SPAN", 2);
+    const int max_stages = env_int("LD_GEMM_STAGES", 16);
+    const int tile_stage_cin = env_int("LD_GEMM_TILE_STAGE_CIN", 32);
+    const int align_loads = env_int("LD_GEMM_ALIGN", 1);
+    if (env_int("LD_GEMM_PROF", 0)) {
+        LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->gemm_prof), plan.convs.size() * 8 * sizeof(unsigned long long)));
+        LD_CUDA_C(cudaMemset(ctx->gemm_prof, 0, plan.convs.size() * 8 * sizeof(unsigned long long)));
+    }
     ctx->convs.resize(plan.convs.size());
     for (size_t li = 0; li < plan.convs.size(); ++li) {
         const auto& cs = plan.convs[li];
@@ -316,57 +360,90 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         ld::GemmLaunch& L = cd.h;
         std::memset(&L, 0, sizeof(L));
         const ConvWeights& w = ctx->weights[cs.conv];
-        L.weights = w.w; L.scale = w.scale; L.shift = w.shift;
+        L.weights = w.w; L.shift = w.shift;
         L.n_jobs = static_cast<int>(cs.jobs.size());
-        L.cin = cs.cin; L.cout = cs.cout; L.n_wtaps = cs.ksize * cs.ksize;
+        L.cin = cs.cin; L.cout = cs.cout; L.n_wtaps = cs.ksize * cs.ksize + (w.has_res ? 1 : 0);
         L.relu = cs.relu; L.wp = cs.wp; L.out_mode = cs.out_mode; L.wp2 = cs.wp2; L.hp = cs.hp;
         cd.wp = cs.wp;
         int ext_max = 0;
+        struct TapInfo { int group[ld::kMaxTaps], off[ld::kMaxTaps], wtap[ld::kMaxTaps]; };
+        std::vector<TapInfo> tap_info(L.n_jobs);
         for (int j = 0; j < L.n_jobs; ++j) {
             const auto& js = cs.jobs[j];
             ld::GemmJob& job = L.jobs[j];
             std::vector<ld::TapSpec> taps = js.taps;
+            if (js.res_plane >= 0)   // residual add = identity-weight tap on the residual plane (weight slab ksize*ksize)
+                taps.push_back({js.res_plane, js.res_shift, cs.ksize * cs.ksize});
             std::sort(taps.begin(), taps.end(), [](const ld::TapSpec& a, const ld::TapSpec& b) {
                 return a.plane != b.plane ? a.plane < b.plane : a.shift < b.shift;
             });
             if (taps.size() > static_cast<size_t>(ld::kMaxTaps)) return cleanup_fail(fail(LD_ERR_INVALID, "too many taps"));
             int g = -1, g_plane = -1, g_min = 0;
+            int group_ext[ld::kMaxGroups] = {0};
+            int* tap_group = tap_info[j].group;
+            int* tap_off = tap_info[j].off;
+            int* tap_w = tap_info[j].wtap;
             for (size_t t = 0; t < taps.size(); ++t) {
-                if (g < 0 || taps[t].plane != g_plane || taps[t].shift - g_min > 136) {
+                if (g < 0 || taps[t].plane != g_plane || taps[t].shift - g_min > group_span + (align_loads ? 7 : 0)) {
                     if (++g >= ld::kMaxGroups) return cleanup_fail(fail(LD_ERR_INVALID, "too many load groups"));
                     g_plane = taps[t].plane; g_min = taps[t].shift;
+                    // start every copy on a 128-byte boundary of the plane (8 pixels): the plane bases are 128 B aligned
+                    // and tiles start at multiples of 128 pixels, so the misalignment is a per-group constant
+                    if (align_loads) g_min -= ((g_min % 8) + 8) % 8;
                     job.groups[g].src = ctx->planes[g_plane].base;
                     job.groups[g].kc_stride = ctx->planes[g_plane].kc_stride;
+                    job.groups[g].tmap = ctx->tmaps + g_plane;
+                    job.groups[g].pixel0 = ld::kGuardRows * ctx->planes[g_plane].wp + 256;
                     job.groups[g].shift = g_min;
-                    job.groups[g].ext = ld::kTileM;
+                    group_ext[g] = ld::kTileM;
                     if (ctx->planes[g_plane].C != cs.cin || ctx->planes[g_plane].wp != cs.wp)
                         return cleanup_fail(fail(LD_ERR_INVALID, "plan/plane mismatch in " + cs.conv));
                 }
-                job.groups[g].ext = std::max(job.groups[g].ext, ld::kTileM + taps[t].shift - g_min);
-                job.taps[t].group = static_cast<int16_t>(g);
-                job.taps[t].off = static_cast<int16_t>(taps[t].shift - g_min);
-                job.taps[t].wtap = static_cast<int16_t>(taps[t].wtap);
-                job.tap_a16[t] = static_cast<uint16_t>(taps[t].shift - g_min);
-                job.tap_b16[t] = static_cast<uint16_t>(taps[t].wtap * (cs.cin / 8) * cs.cout);
-                job.group_taps[g] = static_cast<uint8_t>(job.group_taps[g] + 1);
+                group_ext[g] = std::max(group_ext[g], ld::kTileM + taps[t].shift - g_min);
+                tap_group[t] = g;
+                tap_off[t] = taps[t].shift - g_min;
+                tap_w[t] = taps[t].wtap;
             }
             job.n_groups = g + 1;
             job.n_taps = static_cast<int>(taps.size());
-            for (int q = 0; q < job.n_groups; ++q) ext_max = std::max(ext_max, job.groups[q].ext);
+            for (int q = 0; q < job.n_groups; ++q) ext_max = std::max(ext_max, group_ext[q]);
             job.out0 = ctx->planes[js.out0].base;
             job.out1 = js.out1 >= 0 ? ctx->planes[js.out1].base : nullptr;
             job.out_kc_stride = ctx->planes[js.out0].kc_stride;
-            if (js.res_plane >= 0) {
-                job.res = ctx->planes[js.res_plane].base;
-                job.res_kc_stride = ctx->planes[js.res_plane].kc_stride;
-                job.res_shift = js.res_shift;
-            }
         }
-        L.ext_alloc = (ext_max + 7) & ~7;
-        L.n_stages = ld::gemm_pick_stages(L.cin, L.cout, L.n_wtaps, L.ext_alloc);
+        L.loader = loader;
+        if (loader == 1) {
+            if (ext_max > ld::kBoxPixels) return cleanup_fail(fail(LD_ERR_INVALID, "tap span exceeds the TMA box in " + cs.conv));
+            L.ext_alloc = ld::kBoxPixels;
+        } else {
+            L.ext_alloc = (ext_max + 7) & ~7;
+        }
+        // small-K layers: one smem stage (one barrier round trip) per TILE instead of per group
+        int max_groups = 1;
+        for (int j = 0; j < L.n_jobs; ++j) max_groups = std::max(max_groups, L.jobs[j].n_groups);
+        L.groups_per_stage = (tile_stage_cin > 0 && L.cin <= tile_stage_cin) ? max_groups : 1;
+        L.wp_magic = static_cast<uint32_t>((1ull << 32) / static_cast<unsigned>(cs.wp)) + 1u;
+        L.n_stages = ld::gemm_pick_stages(L.cin, L.cout, L.n_wtaps, L.ext_alloc, L.groups_per_stage, max_stages);
+        L.prof = ctx->gemm_prof ? ctx->gemm_prof + 8 * li : nullptr;
+        // the tap program the MMA warp executes (ld_types.h: kTapFirst / kTapLast)
+        for (int j = 0; j < L.n_jobs; ++j) {
+            ld::GemmJob& job = L.jobs[j];
+            const TapInfo& ti = tap_info[j];
+            const uint32_t box16 = static_cast<uint32_t>(L.ext_alloc) * (cs.cin / 8);
+            const bool tile_stage = L.groups_per_stage > 1;
+            int last_first = 0;
+            for (int t = 0; t < job.n_taps; ++t) {
+                const uint32_t a16 = (tile_stage ? ti.group[t] * box16 : 0u) + static_cast<uint32_t>(ti.off[t]);
+                const uint32_t b16 = static_cast<uint32_t>(ti.wtap[t]) * (cs.cin / 8) * cs.cout;
+                const bool first = tile_stage ? t == 0 : (t == 0 || ti.group[t] != ti.group[t - 1]);
+                const bool last = tile_stage ? t == job.n_taps - 1 : (t == job.n_taps - 1 || ti.group[t] != ti.group[t + 1]);
+                if (a16 >= (1u << 14) || b16 >= (1u << 14)) return cleanup_fail(fail(LD_ERR_INVALID, "tap offset overflow in " + cs.conv));
+                job.tapw[t] = a16 | (b16 << 14) | (first ? ld::kTapFirst : 0u) | (last ? ld::kTapLast : 0u);
+                if (first) last_first = t;
+            }
+            job.tapw[last_first] |= ld::kTapPass;
+        }
         if (L.n_stages < 2) return cleanup_fail(fail(LD_ERR_INVALID, "conv " + cs.conv + " does not fit in shared memory"));
-        LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&cd.d), sizeof(ld::GemmLaunch)));
-        LD_CUDA_C(cudaMemcpy(cd.d, &L, sizeof(L), cudaMemcpyHostToDevice));
     }
     // stem
     ctx->stem.n_jobs = static_cast<int>(plan.stem.size());
@@ -409,12 +486,12 @@ void ld_destroy(ld_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->workspace) cudaFree(ctx->workspace);
+    if (ctx->tmaps) cudaFree(ctx->tmaps);
+    if (ctx->gemm_prof) cudaFree(ctx->gemm_prof);
     for (auto& kv : ctx->weights) {
         if (kv.second.w) cudaFree(kv.second.w);
-        if (kv.second.scale) cudaFree(kv.second.scale);
         if (kv.second.shift) cudaFree(kv.second.shift);
     }
-    for (auto& c : ctx->convs) if (c.d) cudaFree(c.d);
     if (ctx->stem_params) cudaFree(ctx->stem_params);
     if (ctx->head_params) cudaFree(ctx->head_params);
     if (ctx->fbank_tables) cudaFree(ctx->fbank_tables);
@@ -451,17 +528,20 @@ int ld_resnet_load_weights(ld_ctx* ctx, const ld_tensor* t, int32_t n) {
         if (b && b->numel != cw.cout) return fail(LD_ERR_INVALID, "mis-sized " + cw.conv + ".bias");
         if (int r = fold_bn(t, n, cw.bn, b ? b->data : nullptr, cw.cout, scale, shift)) return r;
         // (out, in, kh, kw) fp32 -> [tap][in/8][out][8] fp16: the K-major SWIZZLE_NONE B operand
-        std::vector<__half> packed(static_cast<size_t>(taps) * cw.cin * cw.cout);
+        std::vector<__half> packed(static_cast<size_t>(taps + (cw.has_res ? 1 : 0)) * cw.cin * cw.cout, __float2half_rn(0.f));
+        if (cw.has_res)
+            for (int c = 0; c < cw.cout; ++c)   // identity slab [cin/8][cout][8]
+                packed[((static_cast<size_t>(taps) * (cw.cin / 8) + c / 8) * cw.cout + c) * 8 + (c % 8)] = __float2half_rn(1.f);
         for (int tap = 0; tap < taps; ++tap)
             for (int kc = 0; kc < cw.cin / 8; ++kc)
                 for (int o = 0; o < cw.cout; ++o)
                     for (int e = 0; e < 8; ++e) {
                         const int i = kc * 8 + e;
-                        const float v = w->data[(static_cast<size_t>(o) * cw.cin + i) * taps + tap];
+                        // BatchNorm scale folded into the fp16 weight: y = conv(x, w * scale) + shift
+                        const float v = w->data[(static_cast<size_t>(o) * cw.cin + i) * taps + tap] * scale[o];
                         packed[((static_cast<size_t>(tap) * (cw.cin / 8) + kc) * cw.cout + o) * 8 + e] = __float2half_rn(v);
                     }
         LD_CUDA(cudaMemcpy(cw.w, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
-        LD_CUDA(cudaMemcpy(cw.scale, scale.data(), cw.cout * sizeof(float), cudaMemcpyHostToDevice));
         LD_CUDA(cudaMemcpy(cw.shift, shift.data(), cw.cout * sizeof(float), cudaMemcpyHostToDevice));
     }
     // head: bn2 -> linear1 -> bn3 -> relu -> linear2 -> sigmoid
@@ -511,7 +591,7 @@ int ld_resnet_infer_windows(ld_ctx* ctx, const float* feats_d, const int64_t* ch
             const int M = rows * cd.wp;
             const int m_tiles = (M + ld::kTileM - 1) / ld::kTileM;
             Timed t(ctx, stream, 0, 1, static_cast<int>(ci));
-            LD_CUDA(ld::launch_gemm_taps(cd.d, cd.h, m_tiles, M, ctx->num_sms, stream));
+            LD_CUDA(ld::launch_gemm_taps(cd.h, m_tiles, M, ctx->num_sms, stream));
         }
         { Timed t(ctx, stream, 2); LD_CUDA(ld::launch_head(ctx->head, ct, probs_d, row0, nb, stream)); }
     }
@@ -715,6 +795,17 @@ int ld_timing_read(ld_ctx* ctx, double* out_ms, int64_t* out_launches, int32_t r
     return LD_OK;
 }
 int64_t ld_kernel_launches(const ld_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t ld_debug_gemm_counters(ld_ctx* ctx, uint64_t* out, int32_t cap_convs, int32_t reset) {
+    if (!ctx) return fail(LD_ERR_INVALID, "ctx is null");
+    if (!ctx->gemm_prof) return 0;
+    LD_CUDA(cudaSetDevice(ctx->device));
+    LD_CUDA(cudaDeviceSynchronize());
+    const int32_t n = std::min<int32_t>(static_cast<int32_t>(ctx->convs.size()), cap_convs);
+    LD_CUDA(cudaMemcpy(out, ctx->gemm_prof, static_cast<size_t>(n) * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) LD_CUDA(cudaMemset(ctx->gemm_prof, 0, ctx->convs.size() * 8 * sizeof(unsigned long long)));
+    return static_cast<int32_t>(ctx->convs.size());
+}
 
 int32_t ld_timing_read_convs(ld_ctx* ctx, double* out_ms, int32_t cap, int32_t reset) {
     if (!ctx) return fail(LD_ERR_INVALID, "ctx is null");

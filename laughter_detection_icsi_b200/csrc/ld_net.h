@@ -53,9 +53,8 @@ cudaError_t launch_head(const HeadLaunch& L, const ChannelTable& ct, float* prob
                         cudaStream_t stream);
 
 // ld_gemm.cu
-cudaError_t launch_gemm_taps(const GemmLaunch* d_launch, const GemmLaunch& h, int m_tiles, int M, int num_sms,
-                             cudaStream_t stream);
-int gemm_pick_stages(int cin, int cout, int n_wtaps, int ext_alloc);
+cudaError_t launch_gemm_taps(const GemmLaunch& h, int m_tiles, int M, int num_sms, cudaStream_t stream);
+int gemm_pick_stages(int cin, int cout, int n_wtaps, int ext_alloc, int groups_per_stage, int max_stages);
 
 // ld_fbank.cu
 struct FbankMel {           // sparse view of the (257, F) filterbank, built from the caller's matrix

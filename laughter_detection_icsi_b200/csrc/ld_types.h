@@ -19,6 +19,7 @@
 namespace ld {
 
 constexpr int kTileM = 128;      // output pixels per MMA tile (UMMA M)
+constexpr int kBoxPixels = 136;  // pixels per TMA box: a tile plus the +-1 pixel halo of a 3-tap row, rounded to 8
 constexpr int kMaxGroups = 6;    // distinct smem loads per job
 constexpr int kMaxTaps = 10;     // MMA taps per job (3x3 = 9)
 constexpr int kMaxJobs = 16;     // jobs (output planes) per launch
@@ -26,46 +27,42 @@ constexpr int kGuardRows = 104;  // zero guard rows allocated before/after every
 
 enum OutMode : int32_t { OUT_PLAIN = 0, OUT_COLSPLIT = 1 };
 
-// ---- device-side launch description (lives in global memory, copied to smem by the kernel) ----
+// ---- device-side launch description (passed to the kernel BY VALUE as a __grid_constant__ parameter: every field the
+// warp-specialised roles index is then read through the uniform constant path, no shared-memory staging) ----
 struct GemmGroup {
     const __half* src;   // pixel 0, chunk 0 of the source plane
     int64_t kc_stride;   // elements between channel chunks of the source plane
+    const void* tmap;    // CUtensorMap of the source plane: (8 halfs, pixels incl. guards, C/8 chunks), box (8, kBoxPixels, C/8)
+    int32_t pixel0;      // tensor coordinate of the plane's pixel 0 (= guard pixels in front of it)
     int32_t shift;       // first pixel to load relative to the tile's first output pixel
-    int32_t ext;         // pixels to load (128 + span of the taps that share this load)
 };
-struct GemmTap {
-    int16_t group;  // index into groups[]
-    int16_t off;    // pixel offset inside the group's load
-    int16_t wtap;   // weight tap index (ky*3+kx, or 0 for 1x1)
-    int16_t pad_;
-};
-struct GemmJob {
+// One MMA tap as the issuing warp sees it (16-byte smem-descriptor units):
+//   bits 0..13  A offset inside the current smem stage (group slot + pixel shift)    bits 14..27  B offset of the weight slab
+//   bit 28      first tap of a stage: wait for its "full" barrier                   bit 29       last tap of a stage: commit "empty"
+constexpr uint32_t kTapFirst = 1u << 28, kTapLast = 1u << 29;
+constexpr uint32_t kTapPass = 1u << 30;  // this tap's wait is the tile's last one: the next issuer warp may start waiting
+constexpr int kTapWords = 12;  // kMaxTaps rounded up to whole 16-byte loads
+struct alignas(16) GemmJob {
+    uint32_t tapw[kTapWords];
     GemmGroup groups[kMaxGroups];
-    GemmTap taps[kMaxTaps];
-    // MMA-issue view of the taps, in smem-descriptor units (16 bytes), ordered by group:
-    uint16_t tap_a16[kMaxTaps];      // pixel offset of the tap inside its group's load (1 pixel = 16 B per chunk)
-    uint16_t tap_b16[kMaxTaps + 2];  // offset of the tap's weight slab inside the weight block
-    uint8_t group_taps[kMaxGroups + 2];  // taps per group
     int32_t n_groups, n_taps;
     __half* out0;  // PLAIN: the plane; COLSPLIT: even-column plane
     __half* out1;  // COLSPLIT: odd-column plane
     int64_t out_kc_stride;
-    const __half* res;  // residual plane (same geometry as the job's output pixels) or null
-    int64_t res_kc_stride;
-    int32_t res_shift;
-    int32_t pad_;
 };
 struct GemmLaunch {
     GemmJob jobs[kMaxJobs];
-    const __half* weights;  // [n_wtaps][cin/8][cout][8] fp16
-    const float* scale;     // [cout] folded BatchNorm scale
+    const __half* weights;  // [n_wtaps][cin/8][cout][8] fp16, BatchNorm scale folded in
     const float* shift;     // [cout] folded BatchNorm shift (+ conv bias)
     int32_t n_jobs, cin, cout, n_wtaps;
     int32_t relu, wp, out_mode, wp2;
-    int32_t ext_alloc;  // pixels reserved per smem stage (>= every group's ext, multiple of 8)
+    int32_t ext_alloc;  // pixels per loaded group (>= every group's extent, multiple of 8)
     int32_t hp;         // >0: rows per image incl. 2 pad rows (dense layout), pad rows forced to zero
     int32_t n_stages;
-    int32_t pad_;
+    int32_t loader;     // 0: one bulk copy per channel chunk; 1: one TMA tensor copy per group
+    int32_t groups_per_stage;  // 1: every group has its own smem stage/barrier; >1: a stage holds all groups of a tile
+    uint32_t wp_magic;  // floor(2^32 / wp) + 1: row = umulhi(pixel, wp_magic)
+    unsigned long long* prof;  // optional: 8 cycle counters per launch (see ld_gemm.cu), null = off
 };
 
 // ---- host-side plan (plane ids instead of pointers) ----

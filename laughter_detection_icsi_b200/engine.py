@@ -247,6 +247,15 @@ class Engine:
         names = [c["conv"] for c in _native.plan_json(self.cfg)["convs"]]
         return [(names[i], ms[i]) for i in range(n)]
 
+    def gemm_counters(self, reset=True):
+        """LD_GEMM_PROF=1 only: [(conv name, [8 cycle counters])], see include/ld_b200.h."""
+        buf = (ctypes.c_uint64 * (64 * 8))()
+        n = self.lib.ld_debug_gemm_counters(self._h, buf, 64, int(bool(reset)))
+        if n < 0:
+            check(n)
+        names = [c["conv"] for c in _native.plan_json(self.cfg)["convs"]]
+        return [(names[i], [int(buf[i * 8 + k]) for k in range(8)]) for i in range(n)]
+
     @property
     def kernel_launches(self):
         return int(self.lib.ld_kernel_launches(self._h))

@@ -76,7 +76,7 @@ class PlanEmulator:
             bias = self.sd.get(c["conv"] + ".bias")
             s, sh = fold_bn(self.sd, c["bn"], bias)
             k = c["ksize"]
-            wtaps = self._q(wt.reshape(c["cout"], c["cin"], k * k))
+            wtaps = self._q(wt.reshape(c["cout"], c["cin"], k * k) * s[:, None, None])  # BN scale folded into fp16 weights
             wp = c["wp"]
             M = rows * wp
             col = torch.arange(M) % wp
@@ -87,7 +87,7 @@ class PlanEmulator:
                     pw, g = self.geom[plane]
                     assert pw == wp
                     acc += self.planes[plane][g + shift:g + shift + M] @ wtaps[:, :, wtap].T
-                y = acc * s + sh
+                y = acc + sh
                 if job["res"] >= 0:
                     pw, g = self.geom[job["res"]]
                     assert pw == wp

@@ -1,0 +1,58 @@
+"""GEMM tuning sweep on a B200: for each knob setting (environment, read at context creation) time the conv stack on one
+synthetic channel and print per-role cycle counters.  Usage: python tools/gemm_sweep.py [minutes] ; not part of the product."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from laughter_detection_icsi_b200 import synth  # noqa: E402
+from laughter_detection_icsi_b200.engine import Engine  # noqa: E402
+
+NAMES = ["prod_wait", "mma_wait_full", "mma_wait_acc", "mma_issue", "epi_wait", "epi_work", "cta", "tiles"]
+
+
+def run(label, env, minutes, detail=False):
+    for k in ("LD_GEMM_LOADER", "LD_GEMM_SPAN", "LD_GEMM_STAGES", "LD_GEMM_PROF", "LD_GEMM_TILE_STAGE_CIN", "LD_GEMM_ALIGN"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    eng = Engine(0)
+    eng.load_state_dict(synth.synthetic_state_dict())
+    T = int(minutes * 6000)
+    feats = torch.randn(T, 44, device="cuda") * 3 - 4
+    for _ in range(2):
+        eng.infer_windows(feats)
+    torch.cuda.synchronize()
+    eng.timing_read(reset=True); eng.timing_read_convs(reset=True); eng.gemm_counters(reset=True)
+    eng.timing_enable(True)
+    reps = 3
+    for _ in range(reps):
+        eng.infer_windows(feats)
+    torch.cuda.synchronize()
+    eng.timing_enable(False)
+    convs = eng.timing_read_convs(reset=True)
+    t = eng.timing_read(reset=True)
+    total = sum(v for _, v in convs) / reps
+    print(f"== {label}: conv stack {total:.2f} ms per {minutes:g} min channel (stem {t['stem'][0] / reps:.2f} head {t['head'][0] / reps:.2f}) "
+          f"-> {minutes / 60 / (total / 1e3):.2f} audio-h/s conv-only", flush=True)
+    if detail:
+        cnt = dict(eng.gemm_counters())
+        for name, ms in convs:
+            line = f"   {name:22s} {ms / reps:7.3f} ms"
+            c = cnt.get(name)
+            if c and c[6]:
+                cta = c[6]
+                line += "  " + " ".join(f"{n}={c[i] / cta:5.2f}" for i, n in enumerate(NAMES[:6])) + f"  cyc/tile={cta / max(c[7], 1):7.0f}"
+            print(line)
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    minutes = float(sys.argv[1]) if len(sys.argv) > 1 else 10.0
+    run("bulk, span 2, aligned", {"LD_GEMM_PROF": "1"}, minutes, detail=True)
+    run("bulk, span 2, unaligned", {"LD_GEMM_ALIGN": "0"}, minutes)
+    run("bulk, span 136, aligned", {"LD_GEMM_SPAN": "136"}, minutes)
+    run("bulk, span 2, aligned, tile-stage cin<=64", {"LD_GEMM_TILE_STAGE_CIN": "64"}, minutes)
