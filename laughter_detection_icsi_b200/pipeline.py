@@ -41,18 +41,18 @@ class LaughterPipeline:
 
     # --- host in, host out ----------------------------------------------------------------------------
     def instances(self, runs, frames, durations_s):
-        """runs -> per channel {(thr, min_len): [(start_s, end_s)]}, fps = frames / duration as in the reference."""
+        """runs -> per channel {(thr, min_len): float64 array (n, 2) of (start_s, end_s)}, fps = frames / duration as in
+        the reference (segment_laughter.py:103-105).  The run lists arrive in frame order, i.e. already grouped by
+        channel; rows compare equal to the reference's list of tuples (``.tolist()``)."""
         out = [dict() for _ in frames]
+        fps = [frames[c] / float(durations_s[c]) for c in range(len(frames))]
         for (starts, ends, chans), thr in zip(runs, self.thresholds):
-            order = np.argsort(chans, kind="stable")
-            starts, ends, chans = starts[order], ends[order], chans[order]
             bounds = np.searchsorted(chans, np.arange(len(frames) + 1))
             for c in range(len(frames)):
                 s, e = starts[bounds[c]:bounds[c + 1]], ends[bounds[c]:bounds[c + 1]]
-                fps = frames[c] / float(durations_s[c])
                 for ml in self.min_lengths:
-                    a, b = self.engine.filter_min_length(s, e, fps, ml)
-                    out[c][(thr, ml)] = list(zip(a.tolist(), b.tolist()))
+                    a, b = self.engine.filter_min_length(s, e, fps[c], ml)
+                    out[c][(thr, ml)] = np.stack([a, b], axis=1)
         return out
 
     def __call__(self, pcm_host, chan_len, durations_s=None):
