@@ -348,7 +348,8 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
     const int group_span = loader == 1 ? std::min(env_int("LD_GEMM_SPAN", 2), ld::kBoxPixels - ld::kTileM) : env_int("LD_GEMM_SPAN", 2);
     const int max_stages = env_int("LD_GEMM_STAGES", 16);
     const int tile_stage_cin = env_int("LD_GEMM_TILE_STAGE_CIN", 32);
-    const int align_loads = env_int("LD_GEMM_ALIGN", 1);
+    const int align_loads = env_int("LD_GEMM_ALIGN", 0);
+    const int n_rings_max = env_int("LD_GEMM_RINGS", 2);
     if (env_int("LD_GEMM_PROF", 0)) {
         LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->gemm_prof), plan.convs.size() * 8 * sizeof(unsigned long long)));
         LD_CUDA_C(cudaMemset(ctx->gemm_prof, 0, plan.convs.size() * 8 * sizeof(unsigned long long)));
@@ -424,6 +425,13 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         L.groups_per_stage = (tile_stage_cin > 0 && L.cin <= tile_stage_cin) ? max_groups : 1;
         L.wp_magic = static_cast<uint32_t>((1ull << 32) / static_cast<unsigned>(cs.wp)) + 1u;
         L.n_stages = ld::gemm_pick_stages(L.cin, L.cout, L.n_wtaps, L.ext_alloc, L.groups_per_stage, max_stages);
+        {   // two rings when half of the stages still hold a whole tile (tile-stage: one stage; per-group: max_groups)
+            const int need = L.groups_per_stage > 1 ? 1 : max_groups;
+            if (L.n_stages < need) return cleanup_fail(fail(LD_ERR_INVALID, "conv " + cs.conv + ": smem ring shorter than one tile"));
+            // (per-group launches whose half ring would hold less than two tiles measured slower with two rings)
+            L.n_rings = (n_rings_max >= 2 && L.n_stages / 2 >= 2 * need) ? 2 : 1;
+            if (L.n_rings == 2) L.n_stages &= ~1;
+        }
         L.prof = ctx->gemm_prof ? ctx->gemm_prof + 8 * li : nullptr;
         // the tap program the MMA warp executes (ld_types.h: kTapFirst / kTapLast)
         for (int j = 0; j < L.n_jobs; ++j) {

@@ -13,11 +13,11 @@
 // shift (the three kx taps of a conv row, or all nine taps of an interior job).
 //
 // Roles (192 threads, one persistent CTA per SM):
-//   warp 0      producer: cp.async.bulk (UBLKCP) global -> smem ring, mbarrier complete_tx
-//   warps 1..4  MMA issuers: tcgen05.mma kind::f16, M=128 N=cout K=16, accumulators in TMEM; tile i of the CTA belongs
-//               to warp 1 + i % 4 (issuing one MMA costs ~25 dependent instructions of a single thread, far more than
+//   warps 0..1  producers: cp.async.bulk (UBLKCP) global -> smem ring, mbarrier complete_tx
+//   warps 2..5  MMA issuers: tcgen05.mma kind::f16, M=128 N=cout K=16, accumulators in TMEM; tile i of the CTA belongs
+//               to issuer i % 4 (issuing one MMA costs ~25 dependent instructions of a single thread, far more than
 //               the 8..32 cycles a small-N MMA occupies the tensor pipe, so four tiles are issued concurrently)
-//   warps 5..8  epilogue: tcgen05.ld -> BN shift (scale is folded into the weights), ReLU, pad masking -> fp16 stores
+//   warps 6..9  epilogue: tcgen05.ld -> BN shift (scale is folded into the weights), ReLU, pad masking -> fp16 stores
 // The residual add of a ResidualBlock is one more tap: the residual plane times an identity weight slab, accumulated in
 // fp32 by the tensor core (exact), so it travels through the same TMA/smem pipeline as every other operand.
 // The launch description is a __grid_constant__ parameter, so tile/job/tap bookkeeping runs on the uniform datapath.
@@ -29,7 +29,8 @@
 namespace ld {
 
 constexpr int kIssuers = 4;      // MMA-issuing warps: tile i of a CTA is issued by warp 1 + i % 4 into accumulator stage i % 4
-constexpr int kGemmThreads = 32 * (1 + kIssuers + 4);
+constexpr int kProducers = 2;    // producer warps: in tile-stage mode they alternate tiles (stage parity = tile parity)
+constexpr int kGemmThreads = 32 * (kProducers + kIssuers + 4);
 constexpr int kAccStages = kIssuers;  // TMEM accumulator ring: one stage per issuer warp
 constexpr int kAccStride = 64;   // TMEM columns per accumulator stage (cout <= 64)
 constexpr int kTmemCols = kAccStages * kAccStride;
@@ -111,7 +112,7 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
         for (int i = 0; i < kIssuers; ++i) mbar_init(bar_turn + 8 * i, 1);
         mbar_fence_init();
     }
-    if (warp == 1) {
+    if (warp == kProducers) {
         tmem_alloc(smem_u32(tmem_slot), kTmemCols);
         tmem_relinquish();
     }
@@ -129,9 +130,9 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
     unsigned long long* prof = L.prof;
     const bool profiling = prof != nullptr;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ producer
-        if (lane == 0) {
+    if (warp < kProducers) {
+        // ------------------------------------------------------------------ producers
+        if (warp == 0 && lane == 0) {
             constexpr uint32_t tap_bytes = static_cast<uint32_t>(CIN) * COUT * 2;
             mbar_expect_tx(bar_w, tap_bytes * n_wtaps);
             for (int t = 0; t < n_wtaps; ++t)
@@ -140,11 +141,18 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
         }
         const int loader = L.loader;
         const uint32_t lbo_a = static_cast<uint32_t>(ext_alloc) * 16u;  // bytes between channel chunks of a group
-        int stage = 0;
+        // Two independent pipelines: producer w fills ring w (stages [w * ring_n, (w + 1) * ring_n)) with the tiles
+        // it = w, w + 2, ... of the CTA; issuers w and w + 2 drain it.  A ring is filled and drained in tile order by
+        // one producer, so nobody ever waits more than one phase ahead on its parity-tracked barriers.
+        // (n_rings == 1 when half the stages could not hold one tile's groups: producer 0 and all four issuers share one ring)
+        const int n_rings = L.n_rings;
+        const int ring_n = n_stages / n_rings;
+        const int ring0 = warp * ring_n;
+        int stage = 0;       // position inside this producer's ring
         uint32_t phase = 0;
         long long c_wait = 0;
-        TileWalk tw(blockIdx.x, gridDim.x, n_jobs);
-        for (int it = 0; it < my_tiles; ++it, tw.next()) {
+        TileWalk tw(blockIdx.x + warp * gridDim.x, n_rings * gridDim.x, n_jobs);
+        for (int it = warp; it < my_tiles && warp < n_rings; it += n_rings, tw.next()) {
             const GemmJob& job = L.jobs[tw.job];
             const int p0 = tw.mt * kTileM;
             const int n_groups = job.n_groups;
@@ -153,15 +161,15 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
             const long long t0 = profiling ? clock64() : 0;
             if (gps > 1) {
                 if (lane == 0) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(bar_full + 8 * stage, box_bytes * n_groups);
+                    mbar_wait(bar_empty + 8 * (ring0 + stage), phase ^ 1);
+                    mbar_expect_tx(bar_full + 8 * (ring0 + stage), box_bytes * n_groups);
                 }
             } else if (lane < n_groups) {
                 int sg = stage + lane;
                 uint32_t ph = phase;
-                if (sg >= n_stages) { sg -= n_stages; ph ^= 1; }
-                mbar_wait(bar_empty + 8 * sg, ph ^ 1);
-                mbar_expect_tx(bar_full + 8 * sg, box_bytes);
+                if (sg >= ring_n) { sg -= ring_n; ph ^= 1; }
+                mbar_wait(bar_empty + 8 * (ring0 + sg), ph ^ 1);
+                mbar_expect_tx(bar_full + 8 * (ring0 + sg), box_bytes);
             }
             if (profiling) c_wait += clock64() - t0;
             __syncwarp();
@@ -172,12 +180,13 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
                 int sg = stage;
                 uint32_t dst;
                 if (gps > 1) {
-                    dst = stage_addr0 + stage * lay.stage_bytes + g * box_bytes;
+                    dst = stage_addr0 + (ring0 + stage) * lay.stage_bytes + g * box_bytes;
                 } else {
                     sg += g;
-                    if (sg >= n_stages) sg -= n_stages;
-                    dst = stage_addr0 + sg * lay.stage_bytes;
+                    if (sg >= ring_n) sg -= ring_n;
+                    dst = stage_addr0 + (ring0 + sg) * lay.stage_bytes;
                 }
+                sg += ring0;
                 const GemmGroup& grp = job.groups[g];
                 if (loader == 1)   // ONE tensor copy brings the (8 halfs x box pixels x C/8 chunks) box
                     tma_load_3d(dst, grp.tmap, 0, grp.pixel0 + p0 + grp.shift, 0, bar_full + 8 * sg);
@@ -186,12 +195,12 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
                              bar_full + 8 * sg);
             }
             stage += gps > 1 ? 1 : n_groups;
-            if (stage >= n_stages) { stage -= n_stages; phase ^= 1; }
+            if (stage >= ring_n) { stage -= ring_n; phase ^= 1; }
         }
-        if (profiling && lane == 0) atomicAdd(prof + PROF_PROD_WAIT, static_cast<unsigned long long>(c_wait));
-    } else if (warp <= kIssuers) {
+        if (profiling && lane == 0 && warp == 0) atomicAdd(prof + PROF_PROD_WAIT, static_cast<unsigned long long>(c_wait));
+    } else if (warp < kProducers + kIssuers) {
         // ------------------------------------------------------------------ MMA issuers (uniform control flow per warp)
-        const int iw = warp - 1;  // this warp issues tiles iw, iw + 4, ... of the CTA into accumulator stage iw
+        const int iw = warp - kProducers;  // this warp issues tiles iw, iw + 4, ... of the CTA into accumulator stage iw
         constexpr uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(COUT));
         // smem matrix descriptors (see ld_ptx.cuh): only the 14-bit start address in the low word changes per MMA.
         constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);            // SBO = 128 B, descriptor version 1
@@ -202,24 +211,30 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
         const uint32_t stage16 = lay.stage_bytes >> 4;
         const bool leader = elect_one();
         mbar_wait(bar_w, 0);
-        // position of the smem ring at the start of this warp's next tile: stages are consumed in tile order, one per
-        // tile (tile-stage mode) or one per group; the tiles of the other issuers are skipped by adding their counts
+        // issuer iw drains ring iw % 2 together with issuer iw ^ 2: the ring's tiles (it = ring, ring + 2, ...) alternate
+        // between the two; the partner's tiles are skipped by advancing the ring position by their stage count
+        const int n_rings = L.n_rings;
+        const int ipr = kIssuers / n_rings;      // issuers per ring
+        const int ring = iw % n_rings, slot = iw / n_rings;
+        const int next_issuer = ring + n_rings * ((slot + 1) % ipr);
+        const int ring_n = n_stages / n_rings;
+        const int ring0 = ring * ring_n;
         int stage = 0;
         uint32_t phase = 0;
         auto advance = [&](int n) {
             stage += n;
-            while (stage >= n_stages) { stage -= n_stages; phase ^= 1; }
+            while (stage >= ring_n) { stage -= ring_n; phase ^= 1; }
         };
         const int acc = iw;
         uint32_t acc_phase = 0;
-        // "full" barriers are parity-tracked, so a warp must never wait on a stage more than one fill ahead: the
-        // issuers take turns -- warp i starts waiting for operands only after warp i-1 has seen its last stage arrive
+        // "full" barriers are parity-tracked, so a warp must never wait on a stage more than one fill ahead: the two
+        // issuers of a ring take turns -- one starts waiting for operands only after the other has seen its last stage
         uint32_t turn_phase = 0;
         long long c_full = 0, c_acc = 0, c_issue = 0;
-        TileWalk tw(blockIdx.x, gridDim.x, n_jobs);
-        for (int it = 0; it < my_tiles; ++it, tw.next()) {
+        TileWalk tw(blockIdx.x + ring * gridDim.x, n_rings * gridDim.x, n_jobs);
+        for (int it = ring, k = 0; it < my_tiles; it += n_rings, ++k, tw.next()) {
             const GemmJob& job = L.jobs[tw.job];
-            if ((it & (kIssuers - 1)) != iw) {
+            if ((k % ipr) != slot) {
                 advance(gps > 1 ? 1 : job.n_groups);
                 continue;
             }
@@ -232,7 +247,7 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
             }
             const int n_taps = job.n_taps;
             long long t0 = profiling ? clock64() : 0;
-            if (it > 0) {
+            if (k > 0) {
                 mbar_wait(bar_turn + 8 * iw, turn_phase);
                 turn_phase ^= 1;
             }
@@ -247,11 +262,11 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
                 if (t < n_taps) {
                     const uint32_t w = tp[t];
                     if (w & kTapFirst) {
-                        mbar_wait(bar_full + 8 * stage, phase);
+                        mbar_wait(bar_full + 8 * (ring0 + stage), phase);
                         if (profiling) { const long long t1 = clock64(); c_full += t1 - t0; t0 = t1; }
                         tc_fence_after();
-                        a_stage = a_lo0 | ((stage_addr0 >> 4) + stage * stage16);
-                        if ((w & kTapPass) && lane == 0) mbar_arrive(bar_turn + 8 * ((iw + 1) & (kIssuers - 1)));
+                        a_stage = a_lo0 | ((stage_addr0 >> 4) + (ring0 + stage) * stage16);
+                        if ((w & kTapPass) && lane == 0) mbar_arrive(bar_turn + 8 * next_issuer);
                     }
                     const uint32_t a_lo = a_stage + (w & 0x3FFFu);
                     const uint32_t b_lo = b_lo0 + ((w >> 14) & 0x3FFFu);
@@ -262,7 +277,7 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
                         accumulate = 1;
                     }
                     if (w & kTapLast) {
-                        umma_commit_pred(bar_empty + 8 * stage, leader);  // frees the smem stage when these MMAs retire
+                        umma_commit_pred(bar_empty + 8 * (ring0 + stage), leader);  // frees the smem stage when these MMAs retire
                         if (profiling) { const long long t1 = clock64(); c_issue += t1 - t0; t0 = t1; }
                         advance(1);
                     }
@@ -360,7 +375,7 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == kProducers) tmem_dealloc(tmem_base, kTmemCols);
     if (profiling && threadIdx.x == 0) atomicAdd(prof + PROF_CTA, static_cast<unsigned long long>(clock64() - t_cta0));
 }
 
@@ -395,8 +410,9 @@ cudaError_t launch_gemm_taps(const GemmLaunch& h, int m_tiles, int M, int num_sm
 // Chooses the smem ring depth for a launch (host side).
 int gemm_pick_stages(int cin, int cout, int n_wtaps, int ext_alloc, int groups_per_stage, int max_stages) {
     if (max_stages > kMaxStages || max_stages < 2) max_stages = kMaxStages;
-    for (int n = max_stages; n >= 2; --n)
+    for (int n = max_stages; n >= 2; --n) {
         if (gemm_smem_layout(cin, cout, n_wtaps, ext_alloc, groups_per_stage, n).total <= 227u * 1024u) return n;
+    }
     return 0;
 }
 

@@ -62,6 +62,8 @@ struct GemmLaunch {
     int32_t loader;     // 0: one bulk copy per channel chunk; 1: one TMA tensor copy per group
     int32_t groups_per_stage;  // 1: every group has its own smem stage/barrier; >1: a stage holds all groups of a tile
     uint32_t wp_magic;  // floor(2^32 / wp) + 1: row = umulhi(pixel, wp_magic)
+    int32_t n_rings;    // 2: two producer/issuer pipelines over half the stages each; 1: a single ring
+    int32_t pad_;
     unsigned long long* prof;  // optional: 8 cycle counters per launch (see ld_gemm.cu), null = off
 };
 

@@ -14,7 +14,7 @@ NAMES = ["prod_wait", "mma_wait_full", "mma_wait_acc", "mma_issue", "epi_wait", 
 
 
 def run(label, env, minutes, detail=False):
-    for k in ("LD_GEMM_LOADER", "LD_GEMM_SPAN", "LD_GEMM_STAGES", "LD_GEMM_PROF", "LD_GEMM_TILE_STAGE_CIN", "LD_GEMM_ALIGN"):
+    for k in ("LD_GEMM_LOADER", "LD_GEMM_SPAN", "LD_GEMM_STAGES", "LD_GEMM_PROF", "LD_GEMM_TILE_STAGE_CIN", "LD_GEMM_ALIGN", "LD_GEMM_RINGS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     eng = Engine(0)
@@ -52,7 +52,5 @@ def run(label, env, minutes, detail=False):
 
 if __name__ == "__main__":
     minutes = float(sys.argv[1]) if len(sys.argv) > 1 else 10.0
-    run("bulk, span 2, aligned", {"LD_GEMM_PROF": "1"}, minutes, detail=True)
-    run("bulk, span 2, unaligned", {"LD_GEMM_ALIGN": "0"}, minutes)
-    run("bulk, span 136, aligned", {"LD_GEMM_SPAN": "136"}, minutes)
-    run("bulk, span 2, aligned, tile-stage cin<=64", {"LD_GEMM_TILE_STAGE_CIN": "64"}, minutes)
+    run("default", {"LD_GEMM_PROF": "1"}, minutes, detail=True)
+    run("one ring", {"LD_GEMM_RINGS": "1"}, minutes)
