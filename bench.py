@@ -244,6 +244,7 @@ def run_b200(args):
                 "kernel_ms_per_step": gemm_ms / args.steps, "kernel_launches_per_step": gemm_launches / args.steps,
                 "kernel_share_of_step": gemm_ms / ms if ms else None,
                 "per_conv_ms_per_step": {name: round(v / args.steps, 3) for name, v in conv_ms},
+                "class_ms_per_step": {name: round(v[0] / args.steps, 3) for name, v in timing.items()},
                 "peak_source": peaks["source"], "traffic": prof.get("gemm_dram_bytes_per_launch"),
                 "fbank": {"bound": "hbm", "unit": "GB/s", "achieved": 496.0 * windows_per_step * args.steps / (fbank_ms * 1e-3) / 1e9
                           if fbank_ms else None, "peak": peaks["hbm_gbs"], "ms_per_step": fbank_ms / args.steps,
