@@ -128,6 +128,29 @@ LD_API void ld_butter2_lowpass(double cutoff, double* b3, double* a3);
 LD_API int ld_infer_pcm_host(ld_ctx* ctx, const int16_t* pcm_host, const int64_t* chan_len, int32_t n_chan,
                       const float* mel_host, float* probs_host, void* stream);
 
+/* ---- Training (reference train.py:261-297: model(src) in .train() mode, loss.backward()) ------------------------------
+ * ld_train_create allocates the dense training network for batches of up to max_batch windows (bf16 operands, fp32
+ * accumulation and master parameters).  Parameters and gradients travel as ONE flat fp32 device buffer in the order of
+ * ResNetBigger.parameters() (ld_train_table_json lists name/offset/numel, and the BatchNorm modules with the offset of
+ * their batch mean[C] / biased var[C] inside bn_stats, for the running-statistics update the caller performs).
+ * ld_train_forward: x_d (batch,100,44) fp32, mask1_d (batch,48) / mask2_d (batch,32) float 0/1 keep masks of the two dropout
+ * sites (models.py:232,235), dropout_p the rate (kept units are scaled by 1/(1-p)); writes probs_d (batch) = sigmoid
+ * outputs.  ld_train_backward: dprobs_d = dLoss/dprobs (batch); writes grads_d (n_params).  Conv biases that feed a
+ * training-mode BatchNorm have exactly zero gradient. */
+LD_API int ld_train_create(ld_ctx* ctx, int32_t max_batch);
+LD_API int64_t ld_train_table_json(const ld_ctx* ctx, char* buf, int64_t cap);
+LD_API int ld_train_forward(ld_ctx* ctx, const float* params_d, const float* x_d, int32_t batch, const float* mask1_d,
+                     const float* mask2_d, float dropout_p, float* probs_d, float* bn_stats_d, void* stream);
+LD_API int ld_train_backward(ld_ctx* ctx, const float* dprobs_d, float* grads_d, void* stream);
+LD_API int64_t ld_train_kernel_launches(const ld_ctx* ctx);
+/* Debug: sum |value| of every conv output, activation, conv-output gradient and input-gradient plane of the last step. */
+LD_API int32_t ld_train_debug_checksums(ld_ctx* ctx, double* out, int32_t cap);
+/* Debug: one tensor of the last training step as dense (B, C, H, W) fp32 in host memory.  kind 0: conv output z of conv
+ * `index` (order of the parameter table: conv1, block1.0.conv1, block1.0.conv2, ...), 1: activation level, 2: gradient
+ * of a conv output, 3: gradient wrt a level, 4: block g, 5: block dh.  dims4 receives (B, C, H, W).  Returns the element
+ * count (also when out_host is NULL) or -1. */
+LD_API int64_t ld_train_debug_read(ld_ctx* ctx, int32_t kind, int32_t index, float* out_host, int32_t* dims4);
+
 /* Introspection (no GPU needed): JSON description of the streaming plan (planes, conv jobs, taps),
  * consumed by tests/ to check the planner against the reference network on the CPU.  Returns the number
  * of bytes required (including the terminating NUL); writes at most cap bytes. */

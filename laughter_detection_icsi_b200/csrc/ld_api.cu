@@ -16,6 +16,7 @@
 
 #include "../../include/ld_b200.h"
 #include "ld_net.h"
+#include "ld_train.h"
 #include "ld_types.h"
 
 namespace {
@@ -81,6 +82,7 @@ struct ld_ctx {
     uint8_t* workspace = nullptr;
     size_t workspace_bytes = 0;
     CUtensorMap* tmaps = nullptr;  // device array, one TMA descriptor per plane
+    ld::TrainNet* train = nullptr;   // training network (ld_train_create)
     unsigned long long* gemm_prof = nullptr;  // LD_GEMM_PROF=1: 8 cycle counters per conv launch
     std::vector<PlaneDev> planes;
     std::map<std::string, ConvWeights> weights;
@@ -342,15 +344,8 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
     LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->head_params), ctx->head_param_count * sizeof(float)));
 
     // ---- launch tables -----------------------------------------------------------------------------------
-    // tuning knobs (environment, read once per context): operand loader, load-group span, smem ring depth, counters
-    auto env_int = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
-    const int loader = env_int("LD_GEMM_LOADER", 0);
-    const int group_span = loader == 1 ? std::min(env_int("LD_GEMM_SPAN", 2), ld::kBoxPixels - ld::kTileM) : env_int("LD_GEMM_SPAN", 2);
-    const int max_stages = env_int("LD_GEMM_STAGES", 16);
-    const int tile_stage_cin = env_int("LD_GEMM_TILE_STAGE_CIN", 32);
-    const int align_loads = env_int("LD_GEMM_ALIGN", 0);
-    const int n_rings_max = env_int("LD_GEMM_RINGS", 2);
-    if (env_int("LD_GEMM_PROF", 0)) {
+    const ld::GemmTuning tune = ld::gemm_tuning_from_env();
+    if (std::getenv("LD_GEMM_PROF") && std::atoi(std::getenv("LD_GEMM_PROF"))) {
         LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->gemm_prof), plan.convs.size() * 8 * sizeof(unsigned long long)));
         LD_CUDA_C(cudaMemset(ctx->gemm_prof, 0, plan.convs.size() * 8 * sizeof(unsigned long long)));
     }
@@ -362,96 +357,28 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         std::memset(&L, 0, sizeof(L));
         const ConvWeights& w = ctx->weights[cs.conv];
         L.weights = w.w; L.shift = w.shift;
-        L.n_jobs = static_cast<int>(cs.jobs.size());
         L.cin = cs.cin; L.cout = cs.cout; L.n_wtaps = cs.ksize * cs.ksize + (w.has_res ? 1 : 0);
         L.relu = cs.relu; L.wp = cs.wp; L.out_mode = cs.out_mode; L.wp2 = cs.wp2; L.hp = cs.hp;
+        L.mode = 0;
+        L.prof = ctx->gemm_prof ? ctx->gemm_prof + 8 * li : nullptr;
         cd.wp = cs.wp;
-        int ext_max = 0;
-        struct TapInfo { int group[ld::kMaxTaps], off[ld::kMaxTaps], wtap[ld::kMaxTaps]; };
-        std::vector<TapInfo> tap_info(L.n_jobs);
-        for (int j = 0; j < L.n_jobs; ++j) {
+        std::vector<ld::HostJob> jobs(cs.jobs.size());
+        for (size_t j = 0; j < cs.jobs.size(); ++j) {
             const auto& js = cs.jobs[j];
-            ld::GemmJob& job = L.jobs[j];
             std::vector<ld::TapSpec> taps = js.taps;
             if (js.res_plane >= 0)   // residual add = identity-weight tap on the residual plane (weight slab ksize*ksize)
                 taps.push_back({js.res_plane, js.res_shift, cs.ksize * cs.ksize});
-            std::sort(taps.begin(), taps.end(), [](const ld::TapSpec& a, const ld::TapSpec& b) {
-                return a.plane != b.plane ? a.plane < b.plane : a.shift < b.shift;
-            });
-            if (taps.size() > static_cast<size_t>(ld::kMaxTaps)) return cleanup_fail(fail(LD_ERR_INVALID, "too many taps"));
-            int g = -1, g_plane = -1, g_min = 0;
-            int group_ext[ld::kMaxGroups] = {0};
-            int* tap_group = tap_info[j].group;
-            int* tap_off = tap_info[j].off;
-            int* tap_w = tap_info[j].wtap;
-            for (size_t t = 0; t < taps.size(); ++t) {
-                if (g < 0 || taps[t].plane != g_plane || taps[t].shift - g_min > group_span + (align_loads ? 7 : 0)) {
-                    if (++g >= ld::kMaxGroups) return cleanup_fail(fail(LD_ERR_INVALID, "too many load groups"));
-                    g_plane = taps[t].plane; g_min = taps[t].shift;
-                    // start every copy on a 128-byte boundary of the plane (8 pixels): the plane bases are 128 B aligned
-                    // and tiles start at multiples of 128 pixels, so the misalignment is a per-group constant
-                    if (align_loads) g_min -= ((g_min % 8) + 8) % 8;
-                    job.groups[g].src = ctx->planes[g_plane].base;
-                    job.groups[g].kc_stride = ctx->planes[g_plane].kc_stride;
-                    job.groups[g].tmap = ctx->tmaps + g_plane;
-                    job.groups[g].pixel0 = ld::kGuardRows * ctx->planes[g_plane].wp + 256;
-                    job.groups[g].shift = g_min;
-                    group_ext[g] = ld::kTileM;
-                    if (ctx->planes[g_plane].C != cs.cin || ctx->planes[g_plane].wp != cs.wp)
-                        return cleanup_fail(fail(LD_ERR_INVALID, "plan/plane mismatch in " + cs.conv));
-                }
-                group_ext[g] = std::max(group_ext[g], ld::kTileM + taps[t].shift - g_min);
-                tap_group[t] = g;
-                tap_off[t] = taps[t].shift - g_min;
-                tap_w[t] = taps[t].wtap;
+            for (const auto& t : taps) {
+                const PlaneDev& pd = ctx->planes[t.plane];
+                if (pd.C != cs.cin || pd.wp != cs.wp) return cleanup_fail(fail(LD_ERR_INVALID, "plan/plane mismatch in " + cs.conv));
+                jobs[j].taps.push_back({pd.base, pd.kc_stride, ctx->tmaps + t.plane, ld::kGuardRows * pd.wp + 256, t.shift, t.wtap});
             }
-            job.n_groups = g + 1;
-            job.n_taps = static_cast<int>(taps.size());
-            for (int q = 0; q < job.n_groups; ++q) ext_max = std::max(ext_max, group_ext[q]);
-            job.out0 = ctx->planes[js.out0].base;
-            job.out1 = js.out1 >= 0 ? ctx->planes[js.out1].base : nullptr;
-            job.out_kc_stride = ctx->planes[js.out0].kc_stride;
+            jobs[j].out0 = ctx->planes[js.out0].base;
+            jobs[j].out1 = js.out1 >= 0 ? ctx->planes[js.out1].base : nullptr;
+            jobs[j].out_kc_stride = ctx->planes[js.out0].kc_stride;
         }
-        L.loader = loader;
-        if (loader == 1) {
-            if (ext_max > ld::kBoxPixels) return cleanup_fail(fail(LD_ERR_INVALID, "tap span exceeds the TMA box in " + cs.conv));
-            L.ext_alloc = ld::kBoxPixels;
-        } else {
-            L.ext_alloc = (ext_max + 7) & ~7;
-        }
-        // small-K layers: one smem stage (one barrier round trip) per TILE instead of per group
-        int max_groups = 1;
-        for (int j = 0; j < L.n_jobs; ++j) max_groups = std::max(max_groups, L.jobs[j].n_groups);
-        L.groups_per_stage = (tile_stage_cin > 0 && L.cin <= tile_stage_cin) ? max_groups : 1;
-        L.wp_magic = static_cast<uint32_t>((1ull << 32) / static_cast<unsigned>(cs.wp)) + 1u;
-        L.n_stages = ld::gemm_pick_stages(L.cin, L.cout, L.n_wtaps, L.ext_alloc, L.groups_per_stage, max_stages);
-        {   // two rings when half of the stages still hold a whole tile (tile-stage: one stage; per-group: max_groups)
-            const int need = L.groups_per_stage > 1 ? 1 : max_groups;
-            if (L.n_stages < need) return cleanup_fail(fail(LD_ERR_INVALID, "conv " + cs.conv + ": smem ring shorter than one tile"));
-            // (per-group launches whose half ring would hold less than two tiles measured slower with two rings)
-            L.n_rings = (n_rings_max >= 2 && L.n_stages / 2 >= 2 * need) ? 2 : 1;
-            if (L.n_rings == 2) L.n_stages &= ~1;
-        }
-        L.prof = ctx->gemm_prof ? ctx->gemm_prof + 8 * li : nullptr;
-        // the tap program the MMA warp executes (ld_types.h: kTapFirst / kTapLast)
-        for (int j = 0; j < L.n_jobs; ++j) {
-            ld::GemmJob& job = L.jobs[j];
-            const TapInfo& ti = tap_info[j];
-            const uint32_t box16 = static_cast<uint32_t>(L.ext_alloc) * (cs.cin / 8);
-            const bool tile_stage = L.groups_per_stage > 1;
-            int last_first = 0;
-            for (int t = 0; t < job.n_taps; ++t) {
-                const uint32_t a16 = (tile_stage ? ti.group[t] * box16 : 0u) + static_cast<uint32_t>(ti.off[t]);
-                const uint32_t b16 = static_cast<uint32_t>(ti.wtap[t]) * (cs.cin / 8) * cs.cout;
-                const bool first = tile_stage ? t == 0 : (t == 0 || ti.group[t] != ti.group[t - 1]);
-                const bool last = tile_stage ? t == job.n_taps - 1 : (t == job.n_taps - 1 || ti.group[t] != ti.group[t + 1]);
-                if (a16 >= (1u << 14) || b16 >= (1u << 14)) return cleanup_fail(fail(LD_ERR_INVALID, "tap offset overflow in " + cs.conv));
-                job.tapw[t] = a16 | (b16 << 14) | (first ? ld::kTapFirst : 0u) | (last ? ld::kTapLast : 0u);
-                if (first) last_first = t;
-            }
-            job.tapw[last_first] |= ld::kTapPass;
-        }
-        if (L.n_stages < 2) return cleanup_fail(fail(LD_ERR_INVALID, "conv " + cs.conv + " does not fit in shared memory"));
+        std::string err;
+        if (!ld::gemm_build_launch(L, jobs, tune, err)) return cleanup_fail(fail(LD_ERR_INVALID, "conv " + cs.conv + ": " + err));
     }
     // stem
     ctx->stem.n_jobs = static_cast<int>(plan.stem.size());
@@ -494,6 +421,7 @@ void ld_destroy(ld_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->workspace) cudaFree(ctx->workspace);
+    if (ctx->train) ld::train_destroy(ctx->train);
     if (ctx->tmaps) cudaFree(ctx->tmaps);
     if (ctx->gemm_prof) cudaFree(ctx->gemm_prof);
     for (auto& kv : ctx->weights) {
@@ -803,6 +731,78 @@ int ld_timing_read(ld_ctx* ctx, double* out_ms, int64_t* out_launches, int32_t r
     return LD_OK;
 }
 int64_t ld_kernel_launches(const ld_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------- training
+int ld_train_create(ld_ctx* ctx, int32_t max_batch) {
+    if (!ctx) return fail(LD_ERR_INVALID, "ctx is null");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->train) { ld::train_destroy(ctx->train); ctx->train = nullptr; }
+    std::string err;
+    ctx->train = ld::train_create(max_batch, ctx->num_sms, ctx->net, err);
+    if (!ctx->train) return fail(LD_ERR_INVALID, err);
+    return LD_OK;
+}
+
+int64_t ld_train_table_json(const ld_ctx* ctx, char* buf, int64_t cap) {
+    if (!ctx || !ctx->train) { fail(LD_ERR_STATE, "ld_train_create has not been called"); return -1; }
+    std::string s = "{\"params\":[";
+    bool first = true;
+    for (const auto& p : ld::train_param_table(ctx->train)) {
+        s += std::string(first ? "" : ",") + "[\"" + p.name + "\"," + std::to_string(p.offset) + "," + std::to_string(p.numel) + "]";
+        first = false;
+    }
+    s += "],\"batchnorms\":[";
+    first = true;
+    for (const auto& p : ld::train_bn_table(ctx->train)) {
+        s += std::string(first ? "" : ",") + "[\"" + p.name + "\"," + std::to_string(p.offset) + "," + std::to_string(p.numel) + "]";
+        first = false;
+    }
+    s += "],\"n_params\":" + std::to_string(ld::train_num_params(ctx->train)) + ",\"n_bn_stats\":" +
+         std::to_string(ld::train_num_bn_stats(ctx->train)) + "}";
+    const int64_t need = static_cast<int64_t>(s.size()) + 1;
+    if (buf && cap > 0) {
+        const int64_t n = std::min<int64_t>(need, cap);
+        std::memcpy(buf, s.c_str(), static_cast<size_t>(n - 1));
+        buf[n - 1] = 0;
+    }
+    return need;
+}
+
+int ld_train_forward(ld_ctx* ctx, const float* params_d, const float* x_d, int32_t batch, const float* mask1_d, const float* mask2_d,
+                     float dropout_p, float* probs_d, float* bn_stats_d, void* stream_v) {
+    if (!ctx || !params_d || !x_d || !mask1_d || !mask2_d || !probs_d || !bn_stats_d) return fail(LD_ERR_INVALID, "bad arguments");
+    if (!ctx->train) return fail(LD_ERR_STATE, "ld_train_create has not been called");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    std::string err;
+    const cudaError_t e = ld::train_forward(ctx->train, params_d, x_d, batch, mask1_d, mask2_d, dropout_p, probs_d, bn_stats_d,
+                                            static_cast<cudaStream_t>(stream_v), err);
+    if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? LD_ERR_INVALID : LD_ERR_CUDA, err);
+    return LD_OK;
+}
+
+int ld_train_backward(ld_ctx* ctx, const float* dprobs_d, float* grads_d, void* stream_v) {
+    if (!ctx || !dprobs_d || !grads_d) return fail(LD_ERR_INVALID, "bad arguments");
+    if (!ctx->train) return fail(LD_ERR_STATE, "ld_train_create has not been called");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    std::string err;
+    const cudaError_t e = ld::train_backward(ctx->train, dprobs_d, grads_d, static_cast<cudaStream_t>(stream_v), err);
+    if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? LD_ERR_INVALID : LD_ERR_CUDA, err);
+    return LD_OK;
+}
+
+int32_t ld_train_debug_checksums(ld_ctx* ctx, double* out, int32_t cap) {
+    if (!ctx || !ctx->train || !out) return fail(LD_ERR_INVALID, "bad arguments");
+    cudaSetDevice(ctx->device);
+    return ld::train_debug_checksums(ctx->train, out, cap);
+}
+
+int64_t ld_train_debug_read(ld_ctx* ctx, int32_t kind, int32_t index, float* out_host, int32_t* dims4) {
+    if (!ctx || !ctx->train) { fail(LD_ERR_STATE, "ld_train_create has not been called"); return -1; }
+    cudaSetDevice(ctx->device);
+    return ld::train_debug_read(ctx->train, kind, index, out_host, dims4);
+}
+
+int64_t ld_train_kernel_launches(const ld_ctx* ctx) { return (ctx && ctx->train) ? ld::train_kernel_launches(ctx->train) : 0; }
 
 int32_t ld_debug_gemm_counters(ld_ctx* ctx, uint64_t* out, int32_t cap_convs, int32_t reset) {
     if (!ctx) return fail(LD_ERR_INVALID, "ctx is null");

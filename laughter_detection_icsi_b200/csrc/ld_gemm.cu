@@ -23,6 +23,8 @@
 // The launch description is a __grid_constant__ parameter, so tile/job/tap bookkeeping runs on the uniform datapath.
 #include <cstdio>
 
+#include <cuda_bf16.h>
+
 #include "ld_ptx.cuh"
 #include "ld_types.h"
 
@@ -54,7 +56,7 @@ __host__ __device__ inline GemmSmem gemm_smem_layout(int cin, int cout, int n_wt
     s.stage_off = (w_bytes + 127u) & ~127u;
     s.stage_bytes = static_cast<uint32_t>(ext_alloc) * 16u * (cin / 8) * groups_per_stage;
     s.param_off = s.stage_off + n_stages * s.stage_bytes;
-    s.bar_off = s.param_off + static_cast<uint32_t>(cout) * sizeof(float);
+    s.bar_off = s.param_off + 2u * static_cast<uint32_t>((cout + 31) / 32 * 32) * sizeof(float);
     s.bar_off = (s.bar_off + 15u) & ~15u;
     s.total = s.bar_off + (2 * kMaxStages + 2 * kAccStages + 1 + kIssuers) * 8 + 16;
     return s;
@@ -74,7 +76,10 @@ struct TileWalk {
     }
 };
 
-template <int CIN, int COUT>
+// MODE 0: inference -- fp16 operands, epilogue = + folded BatchNorm shift, ReLU, fp16 store (PLAIN or COLSPLIT).
+// MODE 1: training  -- bf16 operands, epilogue = raw conv output as bf16 (PLAIN) and, when L.stats is set, per-channel
+//                      sum / sum of squares of the fp32 accumulators over the real pixels (BatchNorm batch statistics).
+template <int CIN, int COUT, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -98,7 +103,13 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
     const uint32_t bar_w = bar_acc_empty + 8 * kAccStages;
     const uint32_t bar_turn = bar_w + 8;                            // [kIssuers] issuer i may start waiting for operands
 
-    for (int i = threadIdx.x; i < COUT; i += kGemmThreads) s_shift[i] = L.shift[i];
+    // MODE 0: s_shift[COUT] = folded shift.  MODE 1: s_shift[2 * max(COUT, 32)] = per-CTA channel sums, flushed at the end.
+    constexpr int kStatN = (COUT + 31) / 32 * 32;
+    if constexpr (MODE == 0) {
+        for (int i = threadIdx.x; i < COUT; i += kGemmThreads) s_shift[i] = L.shift[i];
+    } else {
+        for (int i = threadIdx.x; i < 2 * kStatN; i += kGemmThreads) s_shift[i] = 0.f;
+    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < n_stages; ++i) {
             mbar_init(bar_full + 8 * i, 1);
@@ -201,7 +212,7 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
     } else if (warp < kProducers + kIssuers) {
         // ------------------------------------------------------------------ MMA issuers (uniform control flow per warp)
         const int iw = warp - kProducers;  // this warp issues tiles iw, iw + 4, ... of the CTA into accumulator stage iw
-        constexpr uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(COUT));
+        constexpr uint32_t idesc = umma_idesc_f16(static_cast<uint32_t>(COUT)) | (MODE == 1 ? ((1u << 7) | (1u << 10)) : 0u);  // bf16 A/B
         // smem matrix descriptors (see ld_ptx.cuh): only the 14-bit start address in the low word changes per MMA.
         constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);            // SBO = 128 B, descriptor version 1
         const uint32_t a_lo0 = (static_cast<uint32_t>(ext_alloc) << 16);  // LBO = ext_alloc * 16 B
@@ -343,24 +354,57 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
             if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);  // accumulator is in registers: hand the stage back
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
 
-            if (do_store) {
+            if constexpr (MODE == 0) {
+                if (do_store) {
 #pragma unroll
-                for (int kc = 0; kc < COUT / 8; ++kc) {
-                    const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + kc * 8);
-                    const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + kc * 8 + 4);
-                    const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-                    uint4 ov;
-                    __half2* oh = reinterpret_cast<__half2*>(&ov);
+                    for (int kc = 0; kc < COUT / 8; ++kc) {
+                        const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + kc * 8);
+                        const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + kc * 8 + 4);
+                        const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+                        uint4 ov;
+                        __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int c = kc * 8 + 2 * e;
-                        float a = __uint_as_float(v[c]) + sh[2 * e];
-                        float b = __uint_as_float(v[c + 1]) + sh[2 * e + 1];
-                        if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                        if (!inner) { a = 0.f; b = 0.f; }
-                        oh[e] = __floats2half2_rn(a, b);
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = kc * 8 + 2 * e;
+                            float a = __uint_as_float(v[c]) + sh[2 * e];
+                            float b = __uint_as_float(v[c + 1]) + sh[2 * e + 1];
+                            if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                            if (!inner) { a = 0.f; b = 0.f; }
+                            oh[e] = __floats2half2_rn(a, b);
+                        }
+                        *reinterpret_cast<uint4*>(dst + kc * out_kc) = ov;
                     }
-                    *reinterpret_cast<uint4*>(dst + kc * out_kc) = ov;
+                }
+            } else {
+                const bool real = valid && inner;
+                if (do_store) {
+#pragma unroll
+                    for (int kc = 0; kc < COUT / 8; ++kc) {
+                        uint4 ov;
+                        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = kc * 8 + 2 * e;
+                            oh[e] = __floats2bfloat162_rn(real ? __uint_as_float(v[c]) : 0.f, real ? __uint_as_float(v[c + 1]) : 0.f);
+                        }
+                        *reinterpret_cast<uint4*>(dst + kc * out_kc) = ov;
+                    }
+                }
+                if (L.stats != nullptr) {   // BatchNorm batch statistics from the fp32 accumulators
+                    float a[kStatN], b[kStatN];
+#pragma unroll
+                    for (int c = 0; c < kStatN; ++c) {
+                        const float z = (c < COUT && real) ? __uint_as_float(v[c < COUT ? c : 0]) : 0.f;
+                        a[c] = z; b[c] = z * z;
+                    }
+                    warp_reduce_channels<kStatN>(a, lane);
+                    warp_reduce_channels<kStatN>(b, lane);
+#pragma unroll
+                    for (int i = 0; i < kStatN / 32; ++i) {
+                        const int c = warp_reduce_channel_of(lane, i, kStatN);
+                        atomicAdd(s_shift + c, a[i]);
+                        atomicAdd(s_shift + kStatN + c, b[i]);
+                    }
                 }
             }
             if (profiling) c_work += clock64() - t0;
@@ -376,34 +420,43 @@ gemm_taps_kernel(const __grid_constant__ GemmLaunch L, int m_tiles, int M) {
     __syncthreads();
     tc_fence_after();
     if (warp == kProducers) tmem_dealloc(tmem_base, kTmemCols);
+    if (MODE == 1 && L.stats != nullptr)   // (the __syncthreads above ordered the shared-memory atomics)
+        for (int i = threadIdx.x; i < 2 * COUT; i += kGemmThreads)
+            atomicAdd(L.stats + i, s_shift[(i < COUT ? 0 : kStatN) + (i < COUT ? i : i - COUT)]);
     if (profiling && threadIdx.x == 0) atomicAdd(prof + PROF_CTA, static_cast<unsigned long long>(clock64() - t_cta0));
 }
 
 // Host launcher.
-template <int CIN, int COUT>
+template <int CIN, int COUT, int MODE>
 static cudaError_t launch_typed(const GemmLaunch& h, int m_tiles, int M, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
     const GemmSmem lay = gemm_smem_layout(CIN, COUT, h.n_wtaps, h.ext_alloc, h.groups_per_stage, h.n_stages);
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_taps_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_taps_kernel<CIN, COUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const long long total = static_cast<long long>(m_tiles) * h.n_jobs;
     if (total <= 0) return cudaSuccess;
     const int grid = static_cast<int>(total < num_sms ? total : num_sms);
-    gemm_taps_kernel<CIN, COUT><<<grid, kGemmThreads, lay.total, stream>>>(h, m_tiles, M);
+    gemm_taps_kernel<CIN, COUT, MODE><<<grid, kGemmThreads, lay.total, stream>>>(h, m_tiles, M);
     return cudaGetLastError();
 }
 
 cudaError_t launch_gemm_taps(const GemmLaunch& h, int m_tiles, int M, int num_sms, cudaStream_t stream) {
 #define LD_GEMM_CASE(ci, co) \
-    if (h.cin == ci && h.cout == co) return launch_typed<ci, co>(h, m_tiles, M, num_sms, stream)
+    if (h.mode == 0 && h.cin == ci && h.cout == co) return launch_typed<ci, co, 0>(h, m_tiles, M, num_sms, stream)
     LD_GEMM_CASE(64, 64); LD_GEMM_CASE(64, 48); LD_GEMM_CASE(64, 32); LD_GEMM_CASE(64, 16);
     LD_GEMM_CASE(48, 64); LD_GEMM_CASE(48, 48); LD_GEMM_CASE(48, 32); LD_GEMM_CASE(48, 16);
     LD_GEMM_CASE(32, 64); LD_GEMM_CASE(32, 48); LD_GEMM_CASE(32, 32); LD_GEMM_CASE(32, 16);
     LD_GEMM_CASE(16, 64); LD_GEMM_CASE(16, 48); LD_GEMM_CASE(16, 32); LD_GEMM_CASE(16, 16);
 #undef LD_GEMM_CASE
+    // training (bf16): forward cin -> cout and dgrad cout -> cin of resnet_base
+#define LD_GEMM_TRAIN(ci, co) \
+    if (h.mode == 1 && h.cin == ci && h.cout == co) return launch_typed<ci, co, 1>(h, m_tiles, M, num_sms, stream)
+    LD_GEMM_TRAIN(64, 64); LD_GEMM_TRAIN(64, 32); LD_GEMM_TRAIN(32, 64); LD_GEMM_TRAIN(32, 32);
+    LD_GEMM_TRAIN(32, 16); LD_GEMM_TRAIN(16, 32); LD_GEMM_TRAIN(16, 16);
+#undef LD_GEMM_TRAIN
     return cudaErrorInvalidValue;
 }
 

@@ -1,6 +1,8 @@
 // Launch descriptions and launcher prototypes of the non-GEMM kernels.
 #pragma once
 #include <cstdint>
+#include <string>
+#include <vector>
 
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -55,6 +57,27 @@ cudaError_t launch_head(const HeadLaunch& L, const ChannelTable& ct, float* prob
 // ld_gemm.cu
 cudaError_t launch_gemm_taps(const GemmLaunch& h, int m_tiles, int M, int num_sms, cudaStream_t stream);
 int gemm_pick_stages(int cin, int cout, int n_wtaps, int ext_alloc, int groups_per_stage, int max_stages);
+
+// ld_launch.cpp
+struct HostTap {
+    const void* src;      // pixel 0, chunk 0 of the source plane
+    long long kc_stride;  // elements between its channel chunks
+    const void* tmap;     // optional CUtensorMap (loader 1)
+    int pixel0;           // tensor coordinate of pixel 0 (loader 1)
+    int shift;            // pixel shift of the tap
+    int wslab;            // weight slab index
+};
+struct HostJob {
+    std::vector<HostTap> taps;
+    void* out0 = nullptr;
+    void* out1 = nullptr;
+    long long out_kc_stride = 0;
+};
+struct GemmTuning {
+    int loader, group_span, max_stages, tile_stage_cin, align_loads, n_rings_max;
+};
+GemmTuning gemm_tuning_from_env();
+bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& jobs, const GemmTuning& tune, std::string& err);
 
 // ld_fbank.cu
 struct FbankMel {           // sparse view of the (257, F) filterbank, built from the caller's matrix

@@ -221,4 +221,31 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t n) {
     return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// Sum over the 32 lanes of a warp of N per-lane values, for all N channels at once: a butterfly in which the lanes
+// trade halves of the vector (N/2 + N/4 + ... shuffles instead of 5 N).  Afterwards lane l holds, in vals[0 .. N/32),
+// the totals of channels  i + bit0(l) N/32 + bit1(l) N/16 + bit2(l) N/8 + bit3(l) N/4 + bit4(l) N/2   (N >= 32).
+template <int N>
+__device__ __forceinline__ void warp_reduce_channels(float (&vals)[N], int lane) {
+    static_assert(N % 32 == 0, "channel count");
+    int n = N / 2;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1, n >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            if (i < n) {
+                const float keep = upper ? vals[i + n] : vals[i];
+                const float send = upper ? vals[i] : vals[i + n];
+                vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+    }
+}
+__device__ __forceinline__ int warp_reduce_channel_of(int lane, int i, int n_channels) {
+    const int u = n_channels / 32;
+    return i + (lane & 1) * u + ((lane >> 1) & 1) * 2 * u + ((lane >> 2) & 1) * 4 * u + ((lane >> 3) & 1) * 8 * u +
+           ((lane >> 4) & 1) * 16 * u;
+}
+
+
 }  // namespace ld

@@ -1,0 +1,52 @@
+// Training path of ResNetBigger (reference train.py:261-297 -> models.py forward in .train() mode + autograd):
+// dense per-sample evaluation, BatchNorm with batch statistics, dropout by caller-provided masks, bf16 operands with
+// fp32 accumulation.  Convolutions (forward and data gradient) run on the same tcgen05 tap-list GEMM kernel as
+// inference (ld_gemm.cu, MODE 1); weight gradients, BatchNorm forward/backward, the stem and the head run on CUDA cores.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "ld_types.h"
+
+namespace ld {
+
+// A training tensor: B images of H x W x C in bf16, channel-chunk planar [C/8][pixels][8] like the inference planes.
+// plain: one plane, image b occupies rows [b*hp, (b+1)*hp) with one zero row above/below and one zero column left/right.
+// quad : four planes by (row parity, column parity) of the real coordinates, each a plain plane of the halved size --
+//        what a stride-2 conv reads with unit-stride taps.
+struct TPlane {
+    __nv_bfloat16* base[4];
+    long long kc_stride;   // elements between channel chunks
+    int H, W, C;
+    int hp, wp;            // rows per image incl. the 2 pad rows, padded width (of each stored plane)
+    int quad;
+};
+
+struct TrainParamInfo {
+    std::string name;
+    long long offset, numel;
+};
+
+class TrainNet;  // opaque (ld_train.cu)
+
+TrainNet* train_create(int max_batch, int num_sms, const NetConfig& cfg, std::string& err);
+void train_destroy(TrainNet* net);
+const std::vector<TrainParamInfo>& train_param_table(const TrainNet* net);
+long long train_num_params(const TrainNet* net);
+const std::vector<TrainParamInfo>& train_bn_table(const TrainNet* net);   // name, offset into bn_stats, C
+int train_num_bn_stats(const TrainNet* net);   // floats of the batch-statistics output: per BatchNorm mean[C] then var[C]
+// params: flat fp32 device buffer in train_param_table order.  x: (B,100,44) fp32 device.  mask1 (B,48), mask2 (B,32):
+// float 0/1 keep masks of the two dropout sites (models.py:232,235).  probs: (B) fp32 out.  bn_stats: device out.
+cudaError_t train_forward(TrainNet* net, const float* params, const float* x, int B, const float* mask1, const float* mask2,
+                          float dropout_p, float* probs, float* bn_stats, cudaStream_t stream, std::string& err);
+// dprobs: dL/dprobs (B) fp32 device.  grads: flat fp32 device buffer (train_param_table order), overwritten.
+cudaError_t train_backward(TrainNet* net, const float* dprobs, float* grads, cudaStream_t stream, std::string& err);
+long long train_kernel_launches(const TrainNet* net);
+int train_debug_checksums(TrainNet* net, double* out, int cap);
+long long train_debug_read(TrainNet* net, int kind, int index, float* out, int* dims4);
+
+}  // namespace ld

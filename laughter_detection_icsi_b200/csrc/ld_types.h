@@ -63,7 +63,8 @@ struct GemmLaunch {
     int32_t groups_per_stage;  // 1: every group has its own smem stage/barrier; >1: a stage holds all groups of a tile
     uint32_t wp_magic;  // floor(2^32 / wp) + 1: row = umulhi(pixel, wp_magic)
     int32_t n_rings;    // 2: two producer/issuer pipelines over half the stages each; 1: a single ring
-    int32_t pad_;
+    int32_t mode;       // 0: inference (fp16, shift + ReLU epilogue); 1: training (bf16, raw output + channel statistics)
+    float* stats;       // mode 1: [2 * cout] per-channel sum and sum of squares (atomically accumulated), or null
     unsigned long long* prof;  // optional: 8 cycle counters per launch (see ld_gemm.cu), null = off
 };
 

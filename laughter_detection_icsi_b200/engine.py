@@ -3,6 +3,7 @@ the hand-written sm_100a kernels behind the C ABI (include/ld_b200.h).  PyTorch 
 memory and streams only.
 """
 import ctypes
+import json
 
 import numpy as np
 import torch
@@ -234,6 +235,52 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.lib.ld_lowpass_filtfilt(self._h, probs.data_ptr(), int(probs.dtype == torch.float64), probs.numel(), b, a,
                                                out.data_ptr(), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------------------------------ training
+    def train_create(self, max_batch=256):
+        """Allocates the dense training network (bf16 operands) for batches of up to max_batch windows."""
+        with torch.cuda.device(self.device):
+            check(self.lib.ld_train_create(self._h, int(max_batch)))
+        need = self.lib.ld_train_table_json(self._h, None, 0)
+        buf = ctypes.create_string_buffer(need)
+        self.lib.ld_train_table_json(self._h, buf, need)
+        self.train_table = json.loads(buf.value.decode())
+        self.train_max_batch = int(max_batch)
+        return self.train_table
+
+    def train_forward(self, flat_params, x, mask1, mask2, dropout_p):
+        """flat_params: (n_params,) fp32 CUDA in ResNetBigger.parameters() order; x: (B,100,44) fp32 CUDA; masks: float 0/1
+        keep masks (B,48), (B,32).  Returns (probs (B,), bn_stats (n_bn_stats,))."""
+        B = x.shape[0]
+        for t in (flat_params, x, mask1, mask2):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError("training tensors must be contiguous float32 CUDA tensors")
+        if flat_params.numel() != self.train_table["n_params"]:
+            raise ValueError("flat parameter vector has the wrong length")
+        probs = torch.empty(B, dtype=torch.float32, device=self.device)
+        bn_stats = torch.empty(self.train_table["n_bn_stats"], dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ld_train_forward(self._h, flat_params.data_ptr(), x.data_ptr(), B, mask1.data_ptr(), mask2.data_ptr(),
+                                            float(dropout_p), probs.data_ptr(), bn_stats.data_ptr(), self._stream()))
+        return probs, bn_stats
+
+    def train_backward(self, dprobs):
+        """dprobs: dLoss/dprobs (B,) fp32 CUDA of the last train_forward.  Returns the flat gradient (n_params,)."""
+        dprobs = dprobs.contiguous().float()
+        grads = torch.empty(self.train_table["n_params"], dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ld_train_backward(self._h, dprobs.data_ptr(), grads.data_ptr(), self._stream()))
+        return grads
+
+    def train_debug_read(self, kind, index):
+        """Dense (B, C, H, W) float32 numpy copy of one training tensor (see ld_train_debug_read)."""
+        dims = (ctypes.c_int32 * 4)()
+        n = self.lib.ld_train_debug_read(self._h, int(kind), int(index), None, dims)
+        if n < 0:
+            raise LdError("no such training tensor")
+        out = np.empty(tuple(dims), dtype=np.float32)
+        self.lib.ld_train_debug_read(self._h, int(kind), int(index), out.ctypes.data_as(ctypes.c_void_p), dims)
         return out
 
     # ------------------------------------------------------------------------------------------ introspection

@@ -31,6 +31,21 @@ class ResidualBlock(nn.Module):
         raise LdError("ResidualBlock is a parameter container; call ResNetBigger.forward (B200 kernels)")
 
 
+class _TrainFunction(torch.autograd.Function):
+    """probs = ResNetBigger_train(flat_params, x): forward/backward on the CUDA training network (ld_train_*)."""
+
+    @staticmethod
+    def forward(ctx, flat, feats, mask1, mask2, p, eng):
+        probs, bn_stats = eng.train_forward(flat.detach().contiguous(), feats, mask1, mask2, p)
+        ctx.eng = eng
+        ctx.mark_non_differentiable(bn_stats)
+        return probs, bn_stats
+
+    @staticmethod
+    def backward(ctx, dprobs, _dstats):
+        return ctx.eng.train_backward(dprobs), None, None, None, None, None
+
+
 class ResNetBigger(nn.Module):
     def __init__(self, num_classes=1, dropout_rate=0.5, linear_layer_size=192, filter_sizes=[64, 32, 16, 16]):
         super().__init__()
@@ -83,11 +98,72 @@ class ResNetBigger(nn.Module):
             self._ld_engine, self._ld_fingerprint = eng, fp
         return eng
 
+    # -------------------------------------------------------------------------------------- training path
+    def _train_engine(self, batch):
+        p = self.conv1.weight
+        if not p.is_cuda:
+            raise LdError("ResNetBigger parameters are not on a CUDA device: call model.set_device('cuda') "
+                          "(this build has no CPU path)")
+        eng = _engine.get_engine(p.device.index or 0, filter_sizes=tuple(self.filter_sizes),
+                                 linear_layer_size=self.linear_layer_size)
+        if getattr(eng, "train_table", None) is None or eng.train_max_batch < batch:
+            eng.train_create(max(int(batch), 256))
+            names = [n for n, _ in self.named_parameters()]
+            table = eng.train_table["params"]
+            if [t[0] for t in table] != names or [t[2] for t in table] != [q.numel() for q in self.parameters()]:
+                raise LdError("parameter order of the module and of the CUDA training network disagree")
+        return eng
+
+    def _forward_train(self, x):
+        """Training-mode forward on the B200 kernels (batch-statistics BatchNorm, dropout); autograd-connected to
+        the module parameters through one flat parameter vector, so loss.backward() fills .grad like the reference."""
+        B = x.shape[0]
+        eng = self._train_engine(B)
+        p = float(self.dropout.p)
+        dev = self.conv1.weight.device
+        if p > 0.0:
+            mask1 = (torch.rand(B, self.linear_layer_size, device=dev) >= p).float()
+            mask2 = (torch.rand(B, 32, device=dev) >= p).float()
+        else:
+            mask1 = torch.ones(B, self.linear_layer_size, device=dev)
+            mask2 = torch.ones(B, 32, device=dev)
+        self._ld_last_masks = (mask1, mask2)
+        flat = torch.cat([q.reshape(-1) for q in self.parameters()])
+        feats = x.detach().float().reshape(B, x.shape[2], x.shape[3]).contiguous()
+        probs, bn_stats = _TrainFunction.apply(flat, feats, mask1, mask2, p, eng)
+        self._update_running_stats(eng, bn_stats, B)
+        return probs.reshape(B, 1)
+
+    @torch.no_grad()
+    def _update_running_stats(self, eng, bn_stats, batch):
+        """nn.BatchNorm's running-statistics update (momentum 0.1, unbiased variance), from the kernel's batch statistics."""
+        modules = dict(self.named_modules())
+        for name, off, C in eng.train_table["batchnorms"]:
+            bn = modules[name]
+            mean, var = bn_stats[off:off + C], bn_stats[off + C:off + 2 * C]
+            n = batch * self._bn_pixels(name) if isinstance(bn, nn.BatchNorm2d) else batch
+            m = bn.momentum if bn.momentum is not None else 0.1
+            bn.running_mean.mul_(1 - m).add_(m * mean)
+            bn.running_var.mul_(1 - m).add_(m * var * (n / max(n - 1, 1)))
+            bn.num_batches_tracked += 1
+
+    def _bn_pixels(self, name):
+        """Spatial positions per sample seen by a BatchNorm2d of the 100 x 44 input."""
+        if name == "bn1":
+            return 100 * 44
+        b = int(name.split(".")[0][len("block"):])
+        return {1: 100 * 44, 2: 50 * 22, 3: 25 * 11, 4: 13 * 6}[b]
+
     def forward(self, x):
-        """x: (B, 1, 100, 44) float -> (B, 1) sigmoid probabilities (eval mode)."""
+        """x: (B, 1, 100, 44) float -> (B, 1) sigmoid probabilities."""
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise ValueError(f"expected input of shape (B, 1, T, F), got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise LdError("input is not on a CUDA device (no CPU path)")
         if self.training:
-            raise LdError("training-mode forward (batch-statistics BatchNorm, dropout, backward) is not part of "
-                          "this round's CUDA path; call model.eval() for inference")
+            if x.shape[2] != 100 or x.shape[3] != 44:
+                raise LdError("ResNetBigger on B200 is built for 100 x 44 windows")
+            return self._forward_train(x)
         if x.dim() != 4 or x.shape[1] != 1:
             raise ValueError(f"expected input of shape (B, 1, T, F), got {tuple(x.shape)}")
         if not x.is_cuda:

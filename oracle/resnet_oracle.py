@@ -130,3 +130,74 @@ def calibrate_head(sd, feats, n_windows=512, target_std=2.0):
     sd["linear2.weight"] = sd["linear2.weight"] * gain
     sd["linear2.bias"] = (sd["linear2.bias"] - float(z.mean())) * gain
     return sd
+
+
+# ------------------------------------------------------------------------------------------------ training mode
+_QUANT = None   # optional rounding model of the CUDA path (bf16 storage), see forward_train(quant=...)
+
+
+def _q(t):
+    """Straight-through rounding: value rounded like the kernels store it, gradient of the identity."""
+    return t if _QUANT is None else t + (_QUANT(t) - t).detach()
+
+
+def _conv_q(x, w, b, **kw):
+    return _q(F.conv2d(_q(x) if _QUANT is None else x, _q(w), None if _QUANT is not None else b, **kw)) if _QUANT is not None \
+        else F.conv2d(x, w, b, **kw)
+
+
+def _bn_train(sd, prefix, x, stats=None):
+    """BatchNorm in .train() mode: batch statistics (biased variance) normalise, like nn.BatchNorm2d/1d."""
+    if stats is not None:
+        dims = [d for d in range(x.dim()) if d != 1]
+        stats[prefix] = (x.mean(dim=dims).detach(), x.var(dim=dims, unbiased=False).detach())
+    return F.batch_norm(x, None, None, sd[prefix + ".weight"], sd[prefix + ".bias"], training=True, eps=1e-5)
+
+
+def _residual_block_train(sd, p, x, stride, stats):
+    h = _q(F.relu(_bn_train(sd, p + ".bn1", _conv_q(x, sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], stride=stride, padding=1), stats)))
+    h = _bn_train(sd, p + ".bn2", _conv_q(h, sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], stride=1, padding=1), stats)
+    if (p + ".shortcut.0.weight") in sd:
+        x = _bn_train(sd, p + ".shortcut.1", _conv_q(x, sd[p + ".shortcut.0.weight"], None, stride=stride), stats)
+    return _q(F.relu(h + x))
+
+
+def forward_train(sd, x, mask1, mask2, dropout_p, stats=None, quant=None):
+    """ResNetBigger.forward in .train() mode (models.py:222-239 with BatchNorm batch statistics and nn.Dropout at
+    :232 and :235), as a function of a state_dict whose tensors may require grad.  The two dropout sites take explicit
+    0/1 keep masks (kept units scaled by 1/(1-p), like nn.Dropout) so that the CUDA path can be given the same masks."""
+    global _QUANT
+    _QUANT = quant   # e.g. lambda t: t.bfloat16().to(t.dtype): rounds conv weights and stored activations like the CUDA path
+    try:
+        return _forward_train(sd, x, mask1, mask2, dropout_p, stats)
+    finally:
+        _QUANT = None
+
+
+def _forward_train(sd, x, mask1, mask2, dropout_p, stats):
+    scale = 1.0 / (1.0 - dropout_p)
+    out = _q(F.relu(_bn_train(sd, "bn1", _q(F.conv2d(x, sd["conv1.weight"], None, stride=1, padding=1)), stats)))
+    for b in range(1, 5):
+        out = _residual_block_train(sd, f"block{b}.0", out, 1 if b == 1 else 2, stats)
+        out = _residual_block_train(sd, f"block{b}.1", out, 1, stats)
+    out = F.avg_pool2d(out, 4)
+    out = out.reshape(out.shape[0], -1)
+    out = _bn_train(sd, "bn2", out, stats) * mask1 * scale
+    out = F.linear(out, sd["linear1.weight"], sd["linear1.bias"])
+    out = _bn_train(sd, "bn3", out, stats) * mask2 * scale
+    out = F.relu(out)
+    out = F.linear(out, sd["linear2.weight"], sd["linear2.bias"])
+    return torch.sigmoid(out)
+
+
+def train_step_reference(sd, x, labels, mask1, mask2, dropout_p, dtype=torch.float64, quant=None):
+    """loss = BCELoss(model(x).squeeze(), labels) and its gradients (train.py:277-289), in `dtype` on the CPU.
+    Returns (probs, loss, {name: grad}, {bn: (batch mean, biased var)})."""
+    params = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in sd.items()
+              if v.dtype.is_floating_point and not k.endswith(("running_mean", "running_var"))}
+    stats = {}
+    probs = forward_train(params, x.to(dtype), mask1.to(dtype), mask2.to(dtype), dropout_p, stats, quant)
+    loss = F.binary_cross_entropy(probs.reshape(-1), labels.to(dtype))
+    loss.backward()
+    grads = {k: (v.grad.detach() if v.grad is not None else torch.zeros_like(v)) for k, v in params.items()}
+    return probs.detach().reshape(-1), float(loss), grads, stats

@@ -45,6 +45,27 @@ def make_resnet():
     print("resnet golden:", y.reshape(-1))
 
 
+def make_resnet_train():
+    """Reference models.py in .train() mode (dropout_rate=0 so that no random mask is involved): outputs, BCE loss and
+    the gradients of a few parameter tensors from the reference module's own autograd -- pins oracle.forward_train."""
+    sd = resnet_oracle.random_state_dict(seed=12)
+    model = ref_models.ResNetBigger(dropout_rate=0.0, linear_layer_size=48, filter_sizes=[64, 32, 16, 16]).double()
+    model.load_state_dict(sd)
+    model.train()
+    rng = np.random.default_rng(13)
+    x = rng.normal(-4.0, 3.0, (8, 1, 100, 44)).astype(np.float32)
+    labels = (rng.uniform(size=8) < 0.5).astype(np.float32)
+    out = model(torch.from_numpy(x).double()).squeeze()
+    loss = torch.nn.BCELoss()(out, torch.from_numpy(labels).double())
+    loss.backward()
+    keep = ["conv1.weight", "bn1.weight", "block1.0.conv2.weight", "block2.0.shortcut.0.weight", "block2.0.shortcut.1.bias",
+            "block3.1.bn2.weight", "block4.0.conv1.weight", "bn2.bias", "linear1.weight", "linear2.bias"]
+    grads = {k.replace(".", "__"): dict(model.named_parameters())[k].grad.numpy() for k in keep}
+    np.savez(os.path.join(HERE, "resnet_train_golden.npz"), sd_seed=12, x_seed=13, probs=out.detach().numpy(), loss=float(loss),
+             running_mean_bn1=model.bn1.running_mean.numpy(), running_var_block2=model.block2[0].bn1.running_var.numpy(), **grads)
+    print("resnet train golden: loss", float(loss))
+
+
 def seg_cases():
     rng = np.random.default_rng(7)
     grid_thr = [round(float(t), 2) for t in np.linspace(0, 0.9, 19)] + [round(float(t), 2) for t in np.linspace(0.91, 1, 10)]
@@ -120,6 +141,7 @@ def make_fbank():
 
 if __name__ == "__main__":
     make_resnet()
+    make_resnet_train()
     make_segmenter()
     make_lowpass()
     make_fbank()

@@ -1,0 +1,252 @@
+"""Training forward/backward on the B200 kernels (ld_train_*) against torch autograd on the CPU restatement of the
+reference's train-mode forward (oracle.resnet_oracle.forward_train), with the same dropout masks injected.
+bf16 operands / fp32 accumulation: the tolerances are relative per-tensor errors, written below."""
+import numpy as np
+import pytest
+import torch
+
+from laughter_detection_icsi_b200 import models
+from laughter_detection_icsi_b200.engine import get_engine
+from oracle import resnet_oracle
+
+pytestmark = pytest.mark.gpu
+
+PROB_ATOL = 4e-2        # sigmoid outputs vs fp64: bf16 storage through 20 batch-normalised layers (see the layer-local test)
+STAT_RTOL = 5e-2        # BatchNorm batch mean / variance vs fp64
+
+
+def make_case(seed, B):
+    sd = resnet_oracle.random_state_dict(seed=seed)
+    rng = np.random.default_rng(seed)
+    # windows that differ from each other like real audio does (level, spectral tilt, temporal modulation): train-mode
+    # BatchNorm divides by the ACROSS-BATCH deviation, so near-identical samples would turn rounding noise into signal
+    t = np.arange(100)[None, :, None] / 100.0
+    f = np.arange(44)[None, None, :] / 44.0
+    level = rng.uniform(-9.0, 0.0, (B, 1, 1))
+    tilt = rng.uniform(-6.0, 6.0, (B, 1, 1))
+    mod = rng.uniform(0.0, 4.0, (B, 1, 1)) * np.sin(2 * np.pi * (rng.uniform(1, 6, (B, 1, 1)) * t + rng.uniform(0, 1, (B, 1, 1))))
+    x = level + tilt * (f - 0.5) + mod + rng.normal(0.0, rng.uniform(0.3, 3.0, (B, 1, 1)), (B, 100, 44))
+    x = torch.from_numpy(x.astype(np.float32)).reshape(B, 1, 100, 44)
+    labels = torch.from_numpy((rng.uniform(size=B) < 0.5).astype(np.float32))
+    mask1 = torch.from_numpy((rng.uniform(size=(B, 48)) >= 0.5).astype(np.float32))
+    mask2 = torch.from_numpy((rng.uniform(size=(B, 32)) >= 0.5).astype(np.float32))
+    return sd, x, labels, mask1, mask2
+
+
+def flat_params(eng, sd):
+    return torch.cat([sd[name].reshape(-1).float() for name, _, _ in eng.train_table["params"]]).cuda()
+
+
+@pytest.fixture(scope="module")
+def train_engine():
+    eng = get_engine(0, filter_sizes=(64, 32, 16, 16), linear_layer_size=48)
+    eng.train_create(64)
+    return eng
+
+
+def test_parameter_table_matches_module_order(train_engine):
+    m = models.ResNetBigger(dropout_rate=0.5, linear_layer_size=48, filter_sizes=[64, 32, 16, 16])
+    table = train_engine.train_table
+    assert [t[0] for t in table["params"]] == [n for n, _ in m.named_parameters()]
+    assert [t[2] for t in table["params"]] == [p.numel() for p in m.parameters()]
+    assert table["n_params"] == 221217
+    bn_names = [n for n, mod in m.named_modules() if isinstance(mod, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d))]
+    assert sorted(t[0] for t in table["batchnorms"]) == sorted(bn_names)
+
+
+@pytest.mark.parametrize("seed,B,p", [(5, 16, 0.5), (6, 33, 0.0)])
+def test_train_forward_backward_matches_autograd(train_engine, seed, B, p):
+    sd, x, labels, mask1, mask2 = make_case(seed, B)
+    if p == 0.0:
+        mask1, mask2 = torch.ones_like(mask1), torch.ones_like(mask2)
+    ref_probs, ref_loss, ref_grads, ref_stats = resnet_oracle.train_step_reference(sd, x, labels, mask1, mask2, p)
+    eng = train_engine
+    flat = flat_params(eng, sd)
+    probs, bn_stats = eng.train_forward(flat, x.reshape(B, 100, 44).cuda().contiguous(), mask1.cuda(), mask2.cuda(), p)
+    assert np.abs(probs.cpu().numpy() - ref_probs.numpy()).max() < PROB_ATOL
+    # BatchNorm batch statistics (what the running-stat update consumes)
+    st = bn_stats.cpu().numpy()
+    for name, off, C in eng.train_table["batchnorms"]:
+        mean, var = ref_stats[name]
+        em = np.abs(st[off:off + C] - mean.numpy()).max() / (np.abs(mean.numpy()).max() + np.sqrt(var.numpy().max()))
+        ev = np.abs(st[off + C:off + 2 * C] - var.numpy()).max() / np.abs(var.numpy()).max()
+        assert em <= STAT_RTOL and ev <= 2 * STAT_RTOL, f"{name}: batch mean error {em:.3e}, variance error {ev:.3e}"
+    # gradients of loss = BCELoss(probs, labels).  End to end the rounding noise of bf16 storage is amplified chaotically by
+    # the batch-normalised stack, so the yardstick is the CPU oracle with the SAME rounding model (bf16-stored weights and
+    # activations, straight-through gradients): the CUDA path must sit as close to fp64 autograd as that model does.
+    pr = probs.detach().clone().requires_grad_(True)
+    loss = torch.nn.functional.binary_cross_entropy(pr, labels.cuda())
+    loss.backward()
+    assert abs(float(loss) - ref_loss) < 2e-2
+    grads = eng.train_backward(pr.grad).cpu().double().numpy()
+    emu = resnet_oracle.train_step_reference(sd, x, labels, mask1, mask2, p, quant=lambda t: t.bfloat16().to(t.dtype))[2]
+    ref_flat = np.concatenate([ref_grads[name].reshape(-1).numpy() for name, _, _ in eng.train_table["params"]])
+    emu_flat = np.concatenate([emu[name].reshape(-1).numpy() for name, _, _ in eng.train_table["params"]])
+    cos = lambda a, b: float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    print(f"all-parameter gradient vs fp64: cuda cos {cos(grads, ref_flat):.4f} rel {rel(grads, ref_flat):.3f} | "
+          f"bf16-model cos {cos(emu_flat, ref_flat):.4f} rel {rel(emu_flat, ref_flat):.3f}")
+    assert cos(grads, ref_flat) > cos(emu_flat, ref_flat) - 0.08
+    assert rel(grads, ref_flat) < 1.5 * rel(emu_flat, ref_flat) + 0.05
+    for name, off, numel in eng.train_table["params"]:
+        if name.endswith("bias") and (".conv1." in name or ".conv2." in name):
+            # a bias in front of a batch-statistics BatchNorm has no gradient
+            assert np.all(grads[off:off + numel] == 0.0) and np.abs(ref_grads[name].numpy()).max() < 1e-9
+
+
+def test_module_training_step_like_train_py():
+    """models.ResNetBigger in .train() mode: loss.backward() fills .grad, clip + Adam step work, running stats move."""
+    torch.manual_seed(0)
+    m = models.ResNetBigger(dropout_rate=0.5, linear_layer_size=48, filter_sizes=[64, 32, 16, 16])
+    m.load_state_dict(resnet_oracle.random_state_dict(seed=8))
+    m.set_device("cuda")
+    m.train()
+    opt = torch.optim.Adam(m.parameters())
+    x = torch.randn(32, 1, 100, 44, device="cuda") * 3 - 4
+    y = (torch.rand(32, device="cuda") < 0.5).float()
+    rm0 = m.block1[0].bn1.running_mean.clone()
+    losses = []
+    for _ in range(3):
+        out = m(x).squeeze()
+        loss = torch.nn.BCELoss()(out, y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+        m.zero_grad()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]          # same batch three times: the loss goes down
+    assert not torch.equal(rm0, m.block1[0].bn1.running_mean)
+    assert int(m.bn1.num_batches_tracked) == 3
+    m.eval()
+    with torch.no_grad():
+        p = m(x)                                                          # eval path still works after training steps
+    assert p.shape == (32, 1) and bool(torch.isfinite(p).all())
+
+
+# ------------------------------------------------------------------------------------------------ layer-local checks
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _bf16(t):
+    return t.float().bfloat16().double()
+
+
+def _bn_fwd(z, gamma, beta):
+    mean = z.mean(dim=(0, 2, 3), keepdim=True)
+    var = z.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
+    xh = (z - mean) / torch.sqrt(var + 1e-5)
+    return xh * gamma.reshape(1, -1, 1, 1) + beta.reshape(1, -1, 1, 1), xh, 1.0 / torch.sqrt(var + 1e-5)
+
+
+def _bn_bwd(g, xh, inv, gamma):
+    n = g.shape[0] * g.shape[2] * g.shape[3]
+    sg = g.sum(dim=(0, 2, 3), keepdim=True)
+    sgx = (g * xh).sum(dim=(0, 2, 3), keepdim=True)
+    dz = gamma.reshape(1, -1, 1, 1) * inv * (g - sg / n - xh * sgx / n)
+    return dz, sgx.reshape(-1), sg.reshape(-1)
+
+
+def test_every_training_kernel_against_torch_on_its_own_inputs(train_engine):
+    """bf16 rounding noise is amplified chaotically by 20 batch-normalised layers (the CPU oracle with bf16-rounded
+    storage deviates from fp64 just as much), so kernel correctness is pinned LOCALLY: every conv output, activation,
+    gradient plane and parameter gradient is recomputed with torch float64 from the tensors the kernels themselves
+    consumed.  Tolerances: 1e-2 relative L2 for bf16-stored planes, 2e-3 for fp32-accumulated parameter gradients."""
+    import torch.nn.functional as F
+    eng = train_engine
+    B, p = 8, 0.5
+    sd, x, labels, mask1, mask2 = make_case(21, B)
+    flat = flat_params(eng, sd)
+    probs, _ = eng.train_forward(flat, x.reshape(B, 100, 44).cuda().contiguous(), mask1.cuda(), mask2.cuda(), p)
+    pr = probs.detach().clone().requires_grad_(True)
+    F.binary_cross_entropy(pr, labels.cuda()).backward()
+    grads = eng.train_backward(pr.grad).cpu().double()
+    gof = {name: grads[off:off + n] for name, off, n in eng.train_table["params"]}
+    rd = lambda kind, idx: torch.from_numpy(eng.train_debug_read(kind, idx)).double()
+    W = {k: v.double() for k, v in sd.items() if v.dtype.is_floating_point}
+    PL, PG = 1e-2, 2e-3
+
+    # stem (fp32 weights and features)
+    z0, y0 = rd(0, 0), rd(1, 0)
+    assert _rel(z0, F.conv2d(x.double(), W["conv1.weight"], None, padding=1)) < PL
+    a0, xh0, inv0 = _bn_fwd(z0, W["bn1.weight"], W["bn1.bias"])
+    assert _rel(y0, F.relu(a0)) < PL
+    ci, level = 1, 0
+    for b in range(1, 5):
+        for r in range(2):
+            pre = f"block{b}.{r}"
+            k = (b - 1) * 2 + r
+            stride = 2 if (b > 1 and r == 0) else 1
+            has_sc = (pre + ".shortcut.0.weight") in W
+            xin, h, y = rd(1, level), rd(1, level + 1), rd(1, level + 2)
+            z1, z2 = rd(0, ci), rd(0, ci + 1)
+            zs = rd(0, ci + 2) if has_sc else None
+            w1, w2 = _bf16(W[pre + ".conv1.weight"]), _bf16(W[pre + ".conv2.weight"])
+            # ---- forward
+            assert _rel(z1, F.conv2d(xin, w1, None, stride=stride, padding=1)) < PL, pre + " conv1"
+            a1, xh1, inv1 = _bn_fwd(z1, W[pre + ".bn1.weight"], W[pre + ".bn1.bias"])
+            assert _rel(h, F.relu(a1)) < PL, pre + " bn1"
+            assert _rel(z2, F.conv2d(h, w2, None, padding=1)) < PL, pre + " conv2"
+            a2, xh2, inv2 = _bn_fwd(z2, W[pre + ".bn2.weight"], W[pre + ".bn2.bias"])
+            if has_sc:
+                ws = _bf16(W[pre + ".shortcut.0.weight"])
+                assert _rel(zs, F.conv2d(xin, ws, None, stride=stride)) < PL, pre + " shortcut"
+                a_s, xhs, invs = _bn_fwd(zs, W[pre + ".shortcut.1.weight"], W[pre + ".shortcut.1.bias"])
+                res = a_s
+            else:
+                res = xin
+            assert _rel(y, F.relu(a2 + res)) < PL, pre + " output"
+            # ---- backward
+            dy, g, dz2, dh, dz1, dx = rd(3, level + 2), rd(4, k), rd(2, ci + 1), rd(5, k), rd(2, ci), rd(3, level)
+            g_ref = dy * (y > 0)
+            assert _rel(g, g_ref) < PL, pre + " g"
+            dz2_ref, dg2, db2 = _bn_bwd(g, xh2, inv2, W[pre + ".bn2.weight"])
+            assert _rel(dz2, dz2_ref) < PL, pre + " dz2"
+            assert _rel(gof[pre + ".bn2.weight"], dg2) < PG and _rel(gof[pre + ".bn2.bias"], db2) < PG, pre + " bn2 grads"
+            assert _rel(dh, F.conv_transpose2d(dz2, w2, padding=1)) < PL, pre + " dh"
+            assert _rel(gof[pre + ".conv2.weight"].reshape(w2.shape), torch.nn.grad.conv2d_weight(h, w2.shape, dz2, padding=1)) < PG, pre + " dW2"
+            dz1_ref, dg1, db1 = _bn_bwd(dh * (h > 0), xh1, inv1, W[pre + ".bn1.weight"])
+            assert _rel(dz1, dz1_ref) < PL, pre + " dz1"
+            assert _rel(gof[pre + ".bn1.weight"], dg1) < PG and _rel(gof[pre + ".bn1.bias"], db1) < PG, pre + " bn1 grads"
+            assert _rel(gof[pre + ".conv1.weight"].reshape(w1.shape),
+                        torch.nn.grad.conv2d_weight(xin, w1.shape, dz1, stride=stride, padding=1)) < PG, pre + " dW1"
+            opad = (xin.shape[2] - ((z1.shape[2] - 1) * stride + 1), xin.shape[3] - ((z1.shape[3] - 1) * stride + 1))
+            dx_ref = F.conv_transpose2d(dz1, w1, stride=stride, padding=1, output_padding=opad if stride == 2 else 0)
+            if has_sc:
+                dzs = rd(2, ci + 2)
+                dzs_ref, dgs, dbs = _bn_bwd(g, xhs, invs, W[pre + ".shortcut.1.weight"])
+                assert _rel(dzs, dzs_ref) < PL, pre + " dzs"
+                assert _rel(gof[pre + ".shortcut.1.weight"], dgs) < PG and _rel(gof[pre + ".shortcut.1.bias"], dbs) < PG
+                assert _rel(gof[pre + ".shortcut.0.weight"].reshape(ws.shape),
+                            torch.nn.grad.conv2d_weight(xin, ws.shape, dzs, stride=stride)) < PG, pre + " dWs"
+                opad_s = (xin.shape[2] - ((zs.shape[2] - 1) * stride + 1), xin.shape[3] - ((zs.shape[3] - 1) * stride + 1))
+                dx_ref = dx_ref + F.conv_transpose2d(dzs, ws, stride=stride, output_padding=opad_s if stride == 2 else 0)
+            else:
+                dx_ref = dx_ref + g
+            assert _rel(dx, dx_ref) < PL, pre + " dx"
+            ci += 3 if has_sc else 2
+            level += 2
+    # stem backward
+    dy0, dz0 = rd(3, 0), rd(2, 0)
+    dz0_ref, dg0, db0 = _bn_bwd(dy0 * (y0 > 0), xh0, inv0, W["bn1.weight"])
+    assert _rel(dz0, dz0_ref) < PL
+    assert _rel(gof["bn1.weight"], dg0) < PG and _rel(gof["bn1.bias"], db0) < PG
+    assert _rel(gof["conv1.weight"].reshape(64, 1, 3, 3), torch.nn.grad.conv2d_weight(x.double(), (64, 1, 3, 3), dz0, padding=1)) < PG
+    # head (fp32 kernels): forward and backward from the last activation the kernels produced
+    ylast = rd(1, level).requires_grad_(True)
+    hp_ = {k: W[k].clone().requires_grad_(True) for k in ("bn2.weight", "bn2.bias", "bn3.weight", "bn3.bias", "linear1.weight",
+                                                         "linear1.bias", "linear2.weight", "linear2.bias")}
+    o = F.avg_pool2d(ylast, 4).reshape(B, -1)
+    o = F.batch_norm(o, None, None, hp_["bn2.weight"], hp_["bn2.bias"], training=True) * mask1.double() * 2.0
+    o = F.linear(o, hp_["linear1.weight"], hp_["linear1.bias"])
+    o = F.relu(F.batch_norm(o, None, None, hp_["bn3.weight"], hp_["bn3.bias"], training=True) * mask2.double() * 2.0)
+    pref = torch.sigmoid(F.linear(o, hp_["linear2.weight"], hp_["linear2.bias"])).reshape(-1)
+    assert np.abs(probs.cpu().double().numpy() - pref.detach().numpy()).max() < 1e-5
+    F.binary_cross_entropy(pref, labels.double()).backward()
+    # (linear1.bias feeds a batch-statistics BatchNorm: its gradient is analytically zero -- compare absolutely)
+    assert float(gof["linear1.bias"].abs().max()) < 1e-6 and float(hp_["linear1.bias"].grad.abs().max()) < 1e-12
+    head_err = {kname: _rel(gof[kname].reshape(v.shape), v.grad) for kname, v in hp_.items() if kname != "linear1.bias"}
+    print("head gradient errors:", {k: f"{e:.2e}" for k, e in head_err.items()}, "dy_last", f"{_rel(rd(3, level), ylast.grad):.2e}")
+    assert max(head_err.values()) < PG, head_err
+    assert _rel(rd(3, level), ylast.grad) < PL

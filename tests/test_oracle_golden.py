@@ -82,3 +82,23 @@ def test_fbank_oracle_frame_counts_and_silence():
     m = fbank_oracle.mel_matrix_lhotse()
     assert m.shape == (257, 44) and np.all(m[256] == 0) and np.all(m >= 0) and m.max() <= 1.0
     assert np.all((m > 0).sum(axis=1) <= 2)  # triangular bank: a bin feeds at most two filters
+
+
+def test_train_mode_oracle_matches_reference_autograd(golden_dir):
+    """oracle.forward_train + autograd against the reference module in .train() mode (dropout 0)."""
+    g = np.load(os.path.join(golden_dir, "resnet_train_golden.npz"))
+    sd = resnet_oracle.random_state_dict(int(g["sd_seed"]))
+    rng = np.random.default_rng(int(g["x_seed"]))
+    x = torch.from_numpy(rng.normal(-4.0, 3.0, (8, 1, 100, 44)).astype(np.float32))
+    labels = torch.from_numpy((rng.uniform(size=8) < 0.5).astype(np.float32))
+    probs, loss, grads, stats = resnet_oracle.train_step_reference(sd, x, labels, torch.ones(8, 48), torch.ones(8, 32), 0.0)
+    assert np.abs(probs.numpy() - g["probs"]).max() < 1e-12 and abs(loss - float(g["loss"])) < 1e-12
+    for key in g.files:
+        if "__" in key:
+            assert np.abs(grads[key.replace("__", ".")].numpy() - g[key]).max() < 1e-10, key
+    # running statistics the reference module accumulated in that one step: 0.9 * init + 0.1 * batch (unbiased variance)
+    mean, var = stats["bn1"]
+    assert np.abs(0.9 * sd["bn1.running_mean"].double().numpy() + 0.1 * mean.numpy() - g["running_mean_bn1"]).max() < 1e-10
+    n = 8 * 50 * 22
+    var2 = stats["block2.0.bn1"][1].numpy() * n / (n - 1)
+    assert np.abs(0.9 * sd["block2.0.bn1.running_var"].double().numpy() + 0.1 * var2 - g["running_var_block2"]).max() < 1e-10
