@@ -114,6 +114,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # the CPU arm runs once per box
+    torch.set_num_threads(os.cpu_count() or 1)   # torchrun pins OMP_NUM_THREADS=1; the CPU arm uses every host core
     sample_s = args.cpu_sample_seconds
     value, dt = time_cpu_reference(sample_s, args.steps, args.warmup)
     cores = torch.get_num_threads()
@@ -130,6 +131,35 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------- training (secondary)
+def time_training(local_rank, world, batch, steps, warmup):
+    """BASELINE configs 4/5: ResNetBigger forward-backward + clip + Adam on synthetic LAD windows, `batch` per GPU, bf16
+    operands; data parallel = one flat-bucket NCCL all-reduce of the gradients per step.  Every step copies its batch from
+    pinned host memory.  Returns (ms per step on this rank, last loss)."""
+    from laughter_detection_icsi_b200 import models, synth, train as ld_train
+    dev = torch.device("cuda", local_rank)
+    model = models.ResNetBigger(dropout_rate=0.5, linear_layer_size=48, filter_sizes=[64, 32, 16, 16])
+    model.load_state_dict(synth.synthetic_state_dict(head_gain=1.0, head_bias_shift=0.0))
+    model.set_device(dev)
+    opt = torch.optim.Adam(model.parameters())
+    rank = int(os.environ.get("RANK", "0"))
+    batches = []
+    for s in range(4):
+        b = ld_train.synthetic_lad_batch(batch, seed=1000 * rank + s)
+        batches.append({k: v.pin_memory() for k, v in b.items()})
+    loss = 0.0
+    for i in range(warmup):
+        loss = ld_train.train_batch(model, opt, batches[i % 4], dev, world_size=world)[0]
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = ld_train.train_batch(model, opt, batches[i % 4], dev, world_size=world)[0]
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, loss
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
@@ -199,10 +229,15 @@ def run_b200(args):
     d2h = pipe.d2h_bytes()
     n_segments = sum(len(v) for d in inst for v in d.values())
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
+    train_ms, train_loss = (0.0, 0.0)
+    if args.train_steps > 0:
+        barrier()
+        train_ms, train_loss = time_training(local_rank, world, args.train_batch, args.train_steps, 3)
+
+    t = torch.tensor([ms, e2e_s * 1e3, train_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = t.tolist()
+    ms_max, e2e_ms_max, train_ms_max = t.tolist()
 
     if rank == 0:
         peaks = load_peaks()
@@ -251,7 +286,15 @@ def run_b200(args):
                           "note": "K1 is fp32-ALU bound (exact 512-point FFT), see DESIGN.md"},
             },
         }
+        if args.train_steps > 0:
+            line["train"] = {
+                "metric": "training samples/sec (ResNetBigger forward+backward+clip+Adam, bf16 operands)", "value": n_gpus * args.train_batch /
+                (train_ms_max * 1e-3), "unit": "samples/sec", "ms_per_step": train_ms_max, "batch_per_gpu": args.train_batch,
+                "steps": args.train_steps, "last_loss": train_loss, "scaling": "weak",
+                "includes": "H2D of the batch from pinned host memory, forward, backward, flat-bucket gradient all-reduce (N>1), "
+                            "clip_grad_norm_ 1.0, Adam", "data": "synthetic LAD windows (100 x 44 log-mel-like), labels recoverable"}
         if n_gpus == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
             v, dt = time_cpu_reference(args.cpu_sample_seconds, 1, 1)
             line["cpu_baseline"] = {
                 "value": v, "unit": "audio-hours/sec", "cores": torch.get_num_threads(), "kind": "port",
@@ -274,6 +317,8 @@ def main():
     ap.add_argument("--minutes", type=float, default=60.0, help="minutes of audio per channel")
     ap.add_argument("--cpu-sample-seconds", type=float, default=20.0, help="audio seconds per CPU-reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=10, help="timed training steps for the secondary `train` object (0 = skip)")
+    ap.add_argument("--train-batch", type=int, default=256, help="training windows per GPU per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -336,6 +336,10 @@ _engines = {}
 def get_engine(device=0, **kw):
     """Process-wide engine per device (one context per GPU per process)."""
     idx = device if isinstance(device, int) else (torch.device(device).index or 0)
+    full = dict(chunk_rows=0, fbank_preproc=_native.LD_PREPROC_UTTERANCE, filter_sizes=(64, 32, 16, 16), linear_layer_size=48)
+    full.update(kw)
+    full["filter_sizes"] = tuple(int(f) for f in full["filter_sizes"])
+    kw = full
     key = (idx, tuple(sorted(kw.items())))
     if key not in _engines:
         _engines[key] = Engine(idx, **kw)

@@ -46,3 +46,39 @@ def test_two_rank_gather_over_gloo(tmp_path):
 
 def test_single_process_gather_is_identity():
     assert ldd.gather_results(["a", "b"], [1, 0], 2) == ["b", "a"]
+
+
+def _grad_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2))]
+    params[0].grad = torch.full((3, 4), float(rank + 1))
+    params[1].grad = torch.arange(5.0) * (rank + 1)
+    # params[2] has no gradient on any rank: it is left out of the bucket
+    n = ldd.allreduce_gradients(params, world)
+    assert n == 17
+    if rank == 0:
+        torch.save({"g0": params[0].grad, "g1": params[1].grad, "g2": params[2].grad}, out_path)
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_bucket_over_gloo(tmp_path):
+    """The flat-bucket gradient all-reduce used for data-parallel training: mean over ranks, written back in place."""
+    out = str(tmp_path / "grads.pt")
+    mp.spawn(_grad_worker, args=(2, 29431 + os.getpid() % 500, out), nprocs=2, join=True)
+    g = torch.load(out)
+    assert torch.equal(g["g0"], torch.full((3, 4), 1.5)) and torch.equal(g["g1"], torch.arange(5.0) * 1.5) and g["g2"] is None
+    # single process: nothing to do
+    p = torch.nn.Parameter(torch.zeros(2)); p.grad = torch.ones(2)
+    assert ldd.allreduce_gradients([p]) == 0 and torch.equal(p.grad, torch.ones(2))
+
+
+def test_train_mirror_helpers():
+    from laughter_detection_icsi_b200 import train as ld_train
+    b = ld_train.synthetic_lad_batch(16, seed=3)
+    assert b["inputs"].shape == (16, 100, 44) and b["inputs"].dtype == torch.float32 and b["is_laugh"].dtype == torch.int32
+    acc, prec, rec = ld_train._calc_metrics(torch.tensor([0.9, 0.2, 0.8, 0.4]), torch.tensor([1.0, 0.0, 0.0, 1.0]))
+    assert (acc, prec, rec) == (0.5, 0.5, 0.5)
+    args = ld_train.build_parser().parse_args(["--config", "resnet_base", "--checkpoint_dir", "ck"])
+    assert args.num_epochs == 1 and args.dropout_rate == 0.5 and args.gradient_accumulation_steps == 1
