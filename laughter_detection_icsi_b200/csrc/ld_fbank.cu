@@ -18,6 +18,7 @@ namespace ld {
 
 constexpr int kFrameLen = 400, kFrameShift = 160, kFftHalf = 256, kBins = 257;
 constexpr int kFramesPerCta = 16;
+constexpr int kGroupsPerCta = 8;   // 128 frames per CTA: table staging amortised over 8 groups
 constexpr int kSpan = (kFramesPerCta - 1) * kFrameShift + kFrameLen;  // 2800 samples staged per CTA
 constexpr int kMaxFilters = 64;
 constexpr int kMaxMelWeights = 1024;
@@ -80,7 +81,6 @@ fbank_kernel(const int16_t* __restrict__ pcm, long long n_samples, long long n_f
     extern __shared__ __align__(16) uint8_t smem_raw[];
     FbankSmem& S = *reinterpret_cast<FbankSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const long long f0 = static_cast<long long>(blockIdx.x) * kFramesPerCta;
 
     // ---- stage tables and this CTA's sample span ------------------------------------------------------
     for (int i = tid; i < kFrameLen; i += 256) S.window[i] = tables[i];
@@ -92,6 +92,11 @@ fbank_kernel(const int16_t* __restrict__ pcm, long long n_samples, long long n_f
         const int total_w = mel.off[F - 1] + mel.len[F - 1];
         for (int i = tid; i < total_w; i += 256) S.melw[i] = mel.weights[i];
     }
+    // the tables are staged once per CTA; the CTA then walks kGroupsPerCta consecutive groups of 16 frames
+    for (int grp = 0; grp < kGroupsPerCta; ++grp) {
+    const long long f0 = (static_cast<long long>(blockIdx.x) * kGroupsPerCta + grp) * kFramesPerCta;
+    if (f0 >= n_frames) break;
+    if (grp > 0) __syncthreads();   // everyone is done with the previous group's samples / spectra
     float mu = 0.f;
     if (!kPerFrame) {
         // exact integer sum -> mean of the [-1,1) floats (Wav2Win: x - mean(x) over the whole recording)
@@ -117,7 +122,7 @@ fbank_kernel(const int16_t* __restrict__ pcm, long long n_samples, long long n_f
     const int fl = tid >> 4;  // frame within the CTA
     const int t = tid & 15;   // thread within the frame
     const long long frame = f0 + fl;
-    if (frame >= n_frames) return;  // whole 16-thread groups leave together; only __syncwarp below
+    if (frame >= n_frames) continue;  // whole 16-thread groups skip together; only __syncwarp below
     const unsigned gmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
     const float* xs = S.samples + fl * kFrameShift;
 
@@ -183,6 +188,7 @@ fbank_kernel(const int16_t* __restrict__ pcm, long long n_samples, long long n_f
         for (int j = 0; j < S.mel_len[k]; ++j) acc = fmaf(p[j], w[j], acc);
         feats[frame * F + k] = logf(fmaxf(acc, 1.1920928955078125e-07f));  // torch.finfo(float32).eps
     }
+    }  // groups
 }
 
 __global__ void __launch_bounds__(256) pcm_sum_kernel(const int16_t* __restrict__ pcm, long long n,
@@ -229,7 +235,7 @@ cudaError_t launch_fbank(const int16_t* pcm, long long n_samples, long long n_fr
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const unsigned grid = static_cast<unsigned>((n_frames + kFramesPerCta - 1) / kFramesPerCta);
+    const unsigned grid = static_cast<unsigned>((n_frames + kFramesPerCta * kGroupsPerCta - 1) / (kFramesPerCta * kGroupsPerCta));
     if (per_frame)
         fbank_kernel<true><<<grid, 256, sizeof(FbankSmem), stream>>>(pcm, n_samples, n_frames, sum_biased, mel, tables, feats);
     else
