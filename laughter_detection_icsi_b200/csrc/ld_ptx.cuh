@@ -3,6 +3,7 @@
 // Nothing here is generic infrastructure: only what ld_gemm.cu needs.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_runtime.h>
 
 namespace ld {

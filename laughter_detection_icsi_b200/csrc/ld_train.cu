@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -562,6 +563,7 @@ struct ConvHost {
     GemmLaunch fwd{}, bwd{};
     bool has_bwd = false;
     std::vector<HostTap> fwd_taps;  // forward taps (also the X operands of wgrad)
+    WgradLaunch wg{};               // tensor-core weight gradient
 };
 struct BlockHost {
     int conv1 = -1, conv2 = -1, sc = -1;   // conv indices
@@ -595,6 +597,8 @@ public:
     float *dl1 = nullptr, *dd1 = nullptr, *dpool = nullptr;
     TPlane dy_last{};
     GemmTuning tune{};
+    bool wgrad_mma = true;            // LD_WGRAD=cuda selects the CUDA-core weight-gradient kernel instead
+    int max_batch_seen = 0;
     long long launches = 0;
     // per-call state
     int B = 0;
@@ -692,6 +696,7 @@ TrainNet* train_create(int max_batch, int num_sms, const NetConfig& cfg, std::st
     n->max_batch = max_batch; n->num_sms = num_sms; n->cfg = cfg;
     n->tune = gemm_tuning_from_env();
     n->tune.loader = 0;
+    if (const char* v = std::getenv("LD_WGRAD")) n->wgrad_mma = std::string(v) != "cuda";
 
     // ---- topology, parameter table (module registration order of the reference's ResNetBigger) and sizes
     struct LevelSpec { int H, W, C, quad; };
@@ -843,6 +848,46 @@ TrainNet* train_create(int max_batch, int num_sms, const NetConfig& cfg, std::st
         job.out_kc_stride = c.z.kc_stride;
         if (!gemm_build_launch(L, {job}, n->tune, err)) { err = c.name + " forward: " + err; delete n; return nullptr; }
     }
+    // weight-gradient launches (tensor cores, ld_wgrad.cu)
+    for (size_t i = 1; i < n->convs.size(); ++i) {
+        ConvHost& c = n->convs[i];
+        const TPlane& x = n->levels[c.in_level];
+        WgradLaunch& W = c.wg;
+        std::memset(&W, 0, sizeof(W));
+        W.cin = c.cin; W.cout = c.cout; W.n_taps = c.ksize * c.ksize;
+        W.dz = c.dz.base[0]; W.dz_kc_stride = c.dz.kc_stride;
+        const int S = 128 / c.cin, wp = c.z.wp;
+        auto add_groups = [&](int seg_first, int n_real, int px_off, int kx) {
+            for (int p0 = 0; p0 < n_real; p0 += S) {
+                const int g = W.n_grp++;
+                W.grp_seg0[g] = seg_first + p0;
+                W.grp_px_off[g] = px_off;
+                for (int sl = 0; sl < 8; ++sl) W.grp_tap[g][sl] = (sl < S && p0 + sl < n_real) ? (p0 + sl) * c.ksize + kx : -1;
+            }
+        };
+        if (c.ksize == 1) {
+            W.n_seg = 1;
+            W.seg_src[0] = x.base[0]; W.seg_kc_stride[0] = x.kc_stride; W.seg_shift[0] = 0;
+            add_groups(0, 1, 0, 0);
+        } else if (c.stride == 1) {
+            W.n_seg = 3;
+            for (int ky = 0; ky < 3; ++ky) { W.seg_src[ky] = x.base[0]; W.seg_kc_stride[ky] = x.kc_stride; W.seg_shift[ky] = (ky - 1) * wp - 1; }
+            for (int kx = 0; kx < 3; ++kx) add_groups(0, 3, kx, kx);
+        } else {
+            W.n_seg = 6;   // [odd-column planes: ky 0..2][even-column planes: ky 0..2]
+            for (int cpi = 0; cpi < 2; ++cpi)
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int rp = (ky - 1) & 1, di = ky == 0 ? -1 : 0, cp = cpi == 0 ? 1 : 0;
+                    const int sgi = cpi * 3 + ky;
+                    W.seg_src[sgi] = x.base[rp * 2 + cp]; W.seg_kc_stride[sgi] = x.kc_stride;
+                    W.seg_shift[sgi] = di * wp + (cpi == 0 ? -1 : 0);
+                }
+            add_groups(0, 3, 0, 0);   // kx = 0: odd columns, dk = -1
+            add_groups(0, 3, 1, 2);   // kx = 2: odd columns, dk = 0
+            add_groups(3, 3, 0, 1);   // kx = 1: even columns
+        }
+        if (W.n_grp > 6 || !wgrad_plan_smem(W)) { err = c.name + ": weight-gradient launch does not fit"; delete n; return nullptr; }
+    }
     // data-gradient launches: conv2 -> dh ; conv1 (+ shortcut / identity) -> gradient of the block input
     for (auto& blk : n->blocks) {
         {   // conv2: stride 1, dh(p) = sum_t W2_t^T dz2(p - shift_t)
@@ -965,6 +1010,18 @@ cudaError_t run_wgrad_t(TrainNet* n, const ConvHost& c, float* dw, cudaStream_t 
 }
 cudaError_t run_wgrad(TrainNet* n, const ConvHost& c, float* dw, cudaStream_t stream) {
     ++n->launches;
+    if (n->wgrad_mma) {
+        WgradLaunch W = c.wg;
+        W.dw = dw;
+        W.M = static_cast<long long>(n->B) * c.dz.hp * c.dz.wp;
+        // the last pixel tile reads up to 127 pixels past M: planes of images >= B must be zero there.  They are, unless an
+        // earlier step used a larger batch -- then the tail is cleared (rare: training uses one batch size).
+        if (n->B < n->max_batch_seen) {
+            for (int kc = 0; kc < c.cout / 8; ++kc)
+                cudaMemsetAsync(c.dz.base[0] + kc * c.dz.kc_stride + W.M * 8, 0, 128 * 16, stream);
+        }
+        return launch_wgrad_mma(W, n->num_sms, stream);
+    }
 #define LD_WG(ci, co, nt) if (c.cin == ci && c.cout == co && c.ksize * c.ksize == nt) return run_wgrad_t<ci, co, nt>(n, c, dw, stream)
     LD_WG(64, 64, 9); LD_WG(64, 32, 9); LD_WG(64, 32, 1); LD_WG(32, 32, 9); LD_WG(32, 16, 9); LD_WG(32, 16, 1);
     LD_WG(16, 16, 9); LD_WG(16, 16, 1);
@@ -993,6 +1050,7 @@ cudaError_t train_forward(TrainNet* n, const float* params, const float* x, int 
     x = n->x_keep; mask1 = n->mask1_keep; mask2 = n->mask2_keep; params = n->params_keep;
     n->B = B; n->params_d = params; n->x_d = x; n->mask1_d = mask1; n->mask2_d = mask2;
     n->keep_scale = 1.f / (1.f - dropout_p);
+    n->max_batch_seen = std::max(n->max_batch_seen, B);
     LD_TRY(cudaMemsetAsync(n->stats, 0, n->stats_floats * sizeof(float), stream));
     // packed bf16 weights from the fp32 master parameters (they change every optimizer step)
     for (size_t i = 1; i < n->convs.size(); ++i) {

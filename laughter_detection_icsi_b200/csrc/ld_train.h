@@ -31,6 +31,27 @@ struct TrainParamInfo {
     long long offset, numel;
 };
 
+// Launch description of the tensor-core weight-gradient kernel (ld_wgrad.cu), passed by value.
+struct WgradLaunch {
+    const __nv_bfloat16* seg_src[9];   // staged pixel runs of X ("segments"): pixel 0 / chunk 0 of the source plane
+    long long seg_kc_stride[9];
+    int seg_shift[9];                  // first pixel of the run relative to the tile's first pixel
+    int n_seg;
+    const __nv_bfloat16* dz;           // gradient of the conv output (plain plane)
+    long long dz_kc_stride;
+    int grp_seg0[6];                   // MMA group g: A starts at segment grp_seg0[g], pixel grp_px_off[g]
+    int grp_px_off[6];
+    int grp_tap[6][8];                 // weight tap (ky * k + kx) of row block s of the group's accumulator, or -1 (ignored)
+    int n_grp;
+    float* dw;                         // (cout, cin, k, k) fp32, accumulated atomically
+    int n_taps, cin, cout;
+    long long M;                       // pixels of the dZ plane to reduce over
+    int n_stages;
+    uint32_t stage_bytes;
+};
+cudaError_t launch_wgrad_mma(const WgradLaunch& L, int num_sms, cudaStream_t stream);
+bool wgrad_plan_smem(WgradLaunch& L);
+
 class TrainNet;  // opaque (ld_train.cu)
 
 TrainNet* train_create(int max_batch, int num_sms, const NetConfig& cfg, std::string& err);
