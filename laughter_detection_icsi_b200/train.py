@@ -48,7 +48,7 @@ def train_batch(model, optimizer, batch, device, clip=1.0, gradient_accumulation
         torch.nn.utils.clip_grad_norm_(model.parameters(), clip)
         optimizer.step()
         model.zero_grad()
-    return float(loss), acc, prec, recall
+    return float(loss.detach()), acc, prec, recall
 
 
 def synthetic_lad_batch(batch_size, seed, device="cpu"):
