@@ -308,3 +308,40 @@ def test_full_size_channel_properties(engine):
     assert torch.equal(alone[:4900], probs[:4900])  # windows that do not reach past frame 5000
     ref = resnet_oracle.window_probs(sd, feats[59800:].cpu().numpy(), dtype=torch.float64)
     assert np.abs(probs[59800:].cpu().numpy() - ref).max() < 2e-2
+
+
+def test_segment_laughter_cli_end_to_end(tmp_path):
+    """The reference's command line (segment_laughter.py:28-52,199) on a synthetic WAV and checkpoint directory:
+    TextGrid tree output_dir/t_<thr>/l_<min_l>/<basename>.TextGrid with the segments the oracle finds on the same
+    probabilities; settings without instances leave no file (segment_laughter.py:131-132)."""
+    import scipy.io.wavfile
+    from laughter_detection_icsi_b200 import config, load_data, segment_laughter, textgrid
+    from laughter_detection_icsi_b200.utils import torch_utils
+    sd = synth.synthetic_state_dict()
+    m = models.ResNetBigger(dropout_rate=0.0, linear_layer_size=48, filter_sizes=[64, 32, 16, 16])
+    m.load_state_dict(sd)
+    ck = tmp_path / "ck"
+    torch_utils.save_checkpoint(torch_utils.make_state_dict(m, torch.optim.Adam(m.parameters()), 0, 0, np.inf), True, str(ck))
+    pcm = synth.synth_channel(16000 * 12 + 123, meeting=4, channel=2).numpy()
+    wav = tmp_path / "Bmr021_chan3.wav"
+    scipy.io.wavfile.write(str(wav), 16000, pcm)
+    out = tmp_path / "out"
+    segment_laughter.main(["--config", "resnet_base", "--model_path", str(ck), "--input_audio_file", str(wav), "--thresholds", "0.3,0.6,1.0",
+                           "--min_lengths", "0.0,0.2", "--save_to_textgrid", "True", "--save_to_audio_files", "False",
+                           "--output_dir", str(out)])
+    model = segment_laughter.load_model(str(ck), config.MODEL_MAP["resnet_base"], torch.device("cuda"))
+    probs = load_data.infer_audio_file(str(wav), model)
+    fps = len(probs) / (len(pcm) / 16000.0)
+    ref = segmenter_oracle.get_laughter_instances(probs, [0.3, 0.6, 1.0], [0.0, 0.2], fps)
+    assert sum(len(v) for v in ref.values()) > 0
+    for (thr, ml), inst in ref.items():
+        path = out / f"t_{thr}" / f"l_{ml}" / "Bmr021_chan3.TextGrid"
+        assert (out / f"t_{thr}" / f"l_{ml}").is_dir()
+        if not inst:
+            assert not path.exists()
+            continue
+        got = [(s, e) for s, e, t in textgrid.read_intervals(str(path)) if t == "laugh"]
+        assert got == [(float(a), float(b)) for a, b in inst], (thr, ml)
+    with pytest.raises(Exception, match="Model checkpoint not found"):
+        segment_laughter.main(["--config", "resnet_base", "--model_path", str(tmp_path / "nope"), "--input_audio_file", str(wav),
+                               "--output_dir", str(out)])
