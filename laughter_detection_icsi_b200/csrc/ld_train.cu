@@ -194,40 +194,55 @@ stem_wgrad_kernel(const float* __restrict__ x, int B, int H, int W, TPlane dz, f
 }
 
 // ------------------------------------------------------------------------------------------------ BatchNorm forward
-// y = act( gamma * (z - mean) * inv + beta  [+ res] ),  res = plane value (res_mode 1) or bn_s(zs) (res_mode 2).
-// One thread per (real pixel, 8-channel chunk).  z and res planes are plain; y may be plain or quad.
-__global__ void __launch_bounds__(256)
-bn_apply_kernel(TPlane z, BnRef bn, int relu, int res_mode, TPlane res, BnRef bn_res, TPlane y, int B) {
-    const int C = z.C, H = z.H, W = z.W, chunks = C / 8;
-    const long long n = static_cast<long long>(B) * H * W * chunks;
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int kc = static_cast<int>(i % chunks);
-    long long pix = i / chunks;
-    const int c0 = static_cast<int>(pix % W), r0 = static_cast<int>((pix / W) % H), b = static_cast<int>(pix / (static_cast<long long>(W) * H));
-    int which;
-    const long long pz = tpix(z, b, r0, c0, which);
-    float v[8], o[8];
-    load8(z.base[0] + kc * z.kc_stride + pz * 8, v);
-    float rv[8];
-    if (res_mode != 0) load8(res.base[0] + kc * res.kc_stride + tpix(res, b, r0, c0, which) * 8, rv);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int c = kc * 8 + e;
+// Per-channel affine form of a batch-statistics BatchNorm, built once per block in shared memory:
+//   xhat = z * xa + xb   (xa = inv std, xb = -mean * inv std)        y = z * ya + yb   (ya = gamma * xa, yb = beta + gamma * xb)
+struct BnCoef {
+    float xa[64], xb[64], ya[64], yb[64];
+};
+__device__ __forceinline__ void bn_coef_setup(BnCoef& s, const BnRef& bn, int C) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float mean, inv;
         bn_mean_inv(bn, C, c, mean, inv);
-        float a = fmaf((v[e] - mean) * inv, bn.gamma[c], bn.beta[c]);
-        if (res_mode == 1) {
-            a += rv[e];
-        } else if (res_mode == 2) {
-            float ms, is;
-            bn_mean_inv(bn_res, C, c, ms, is);
-            a += fmaf((rv[e] - ms) * is, bn_res.gamma[c], bn_res.beta[c]);
-        }
-        o[e] = relu ? fmaxf(a, 0.f) : a;
+        s.xa[c] = inv; s.xb[c] = -mean * inv;
+        s.ya[c] = bn.gamma[c] * inv; s.yb[c] = fmaf(-mean * inv, bn.gamma[c], bn.beta[c]);
     }
-    const long long py = tpix(y, b, r0, c0, which);
-    store8(y.base[which] + kc * y.kc_stride + py * 8, o);
+}
+__device__ __forceinline__ void decode_item(long long i, int chunks, int W, int H, int& kc, int& b, int& r0, int& c0) {
+    kc = static_cast<int>(i % chunks);
+    const long long pix = i / chunks;
+    c0 = static_cast<int>(pix % W);
+    const long long rest = pix / W;
+    r0 = static_cast<int>(rest % H);
+    b = static_cast<int>(rest / H);
+}
+
+// y = act( bn(z) [+ res] ),  res = plane value (res_mode 1) or bn_s(zs) (res_mode 2).  Grid-stride over
+// (real pixel, 8-channel chunk) items.  z and res planes are plain; y may be plain or quad.
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(TPlane z, BnRef bn, int relu, int res_mode, TPlane res, BnRef bn_res, TPlane y, int B) {
+    __shared__ BnCoef s, sr;
+    const int C = z.C, H = z.H, W = z.W, chunks = C / 8;
+    bn_coef_setup(s, bn, C);
+    if (res_mode == 2) bn_coef_setup(sr, bn_res, C);
+    __syncthreads();
+    const long long n = static_cast<long long>(B) * H * W * chunks;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        int kc, b, r0, c0, which;
+        decode_item(i, chunks, W, H, kc, b, r0, c0);
+        float v[8], o[8], rv[8];
+        load8(z.base[0] + kc * z.kc_stride + tpix(z, b, r0, c0, which) * 8, v);
+        if (res_mode != 0) load8(res.base[0] + kc * res.kc_stride + tpix(res, b, r0, c0, which) * 8, rv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = kc * 8 + e;
+            float a = fmaf(v[e], s.ya[c], s.yb[c]);
+            if (res_mode == 1) a += rv[e];
+            else if (res_mode == 2) a += fmaf(rv[e], sr.ya[c], sr.yb[c]);
+            o[e] = relu ? fmaxf(a, 0.f) : a;
+        }
+        const long long py = tpix(y, b, r0, c0, which);
+        store8(y.base[which] + kc * y.kc_stride + py * 8, o);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ BatchNorm backward
@@ -235,8 +250,10 @@ bn_apply_kernel(TPlane z, BnRef bn, int relu, int res_mode, TPlane res, BnRef bn
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, int B, float* __restrict__ sums /*[2C]*/) {
     __shared__ float s_acc[128];
+    __shared__ BnCoef s;
     const int C = z.C, H = z.H, W = z.W, chunks = C / 8;
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+    bn_coef_setup(s, bn, C);
     __syncthreads();
     const long long P = static_cast<long long>(B) * H * W;
     const long long groups = (P + 31) / 32;
@@ -262,11 +279,10 @@ bn_bwd_reduce_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, int B, f
             load8(z.base[0] + kc * z.kc_stride + tpix(z, b, r0, c0, which) * 8, zz);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                float mean, inv;
-                bn_mean_inv(bn, C, kc * 8 + e, mean, inv);
+                const int c = kc * 8 + e;
                 const float ge = (relu && !(yy[e] > 0.f)) ? 0.f : g[e];
                 sg[e] = ge;
-                sx[e] = ge * (zz[e] - mean) * inv;
+                sx[e] = ge * fmaf(zz[e], s.xa[c], s.xb[c]);
             }
         }
 #pragma unroll
@@ -294,38 +310,56 @@ bn_bwd_reduce_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, int B, f
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, const float* __restrict__ sums, int B, TPlane dz, int write_g,
                     TPlane g_out, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ BnCoef s;
+    __shared__ float s_c1[64], s_c2[64];   // mean(g), mean(g xhat)
     const int C = z.C, H = z.H, W = z.W, chunks = C / 8;
+    bn_coef_setup(s, bn, C);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { s_c1[c] = sums[c] * bn.inv_n; s_c2[c] = sums[C + c] * bn.inv_n; }
     if (blockIdx.x == 0 && threadIdx.x < C) {
         dgamma[threadIdx.x] = sums[C + threadIdx.x];
         dbeta[threadIdx.x] = sums[threadIdx.x];
     }
+    __syncthreads();
     const long long n = static_cast<long long>(B) * H * W * chunks;
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int kc = static_cast<int>(i % chunks);
-    const long long pix = i / chunks;
-    const int c0 = static_cast<int>(pix % W), r0 = static_cast<int>((pix / W) % H), b = static_cast<int>(pix / (static_cast<long long>(W) * H));
-    int which;
-    float g[8], zz[8], yy[8], o[8];
-    const long long pd = tpix(dy, b, r0, c0, which);
-    load8(dy.base[which] + kc * dy.kc_stride + pd * 8, g);
-    if (relu) {
-        const long long py = tpix(y, b, r0, c0, which);
-        load8(y.base[which] + kc * y.kc_stride + py * 8, yy);
-    }
-    const long long pz = tpix(z, b, r0, c0, which);
-    load8(z.base[0] + kc * z.kc_stride + pz * 8, zz);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        int kc, b, r0, c0, which;
+        decode_item(i, chunks, W, H, kc, b, r0, c0);
+        float g[8], zz[8], yy[8], o[8];
+        const long long pd = tpix(dy, b, r0, c0, which);
+        load8(dy.base[which] + kc * dy.kc_stride + pd * 8, g);
+        if (relu) {
+            const long long py = tpix(y, b, r0, c0, which);
+            load8(y.base[which] + kc * y.kc_stride + py * 8, yy);
+        }
+        load8(z.base[0] + kc * z.kc_stride + tpix(z, b, r0, c0, which) * 8, zz);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int c = kc * 8 + e;
-        float mean, inv;
-        bn_mean_inv(bn, C, c, mean, inv);
-        if (relu && !(yy[e] > 0.f)) g[e] = 0.f;
-        const float xh = (zz[e] - mean) * inv;
-        o[e] = bn.gamma[c] * inv * (g[e] - sums[c] * bn.inv_n - xh * sums[C + c] * bn.inv_n);
+        for (int e = 0; e < 8; ++e) {
+            const int c = kc * 8 + e;
+            if (relu && !(yy[e] > 0.f)) g[e] = 0.f;
+            const float xh = fmaf(zz[e], s.xa[c], s.xb[c]);
+            o[e] = s.ya[c] * (g[e] - s_c1[c] - xh * s_c2[c]);
+        }
+        store8(dz.base[0] + kc * dz.kc_stride + tpix(dz, b, r0, c0, which) * 8, o);
+        if (write_g) store8(g_out.base[0] + kc * g_out.kc_stride + tpix(g_out, b, r0, c0, which) * 8, g);
     }
-    store8(dz.base[0] + kc * dz.kc_stride + tpix(dz, b, r0, c0, which) * 8, o);
-    if (write_g) store8(g_out.base[0] + kc * g_out.kc_stride + tpix(g_out, b, r0, c0, which) * 8, g);
+}
+
+// mean / biased variance of every conv BatchNorm from the channel sums, conv bias added back to the mean (the kernels leave
+// it out because it cancels in the normalisation, but the module's running_mean tracks the biased conv output).
+struct BnFinalizeItem {
+    int sums_off, out_off, C;
+    long long bias_off;   // into the parameter vector, or -1
+    float inv_n;
+};
+__global__ void bn_finalize_kernel(const BnFinalizeItem* __restrict__ items, int n_items, const float* __restrict__ stats,
+                                   const float* __restrict__ params, float* __restrict__ bn_stats) {
+    const BnFinalizeItem it = items[blockIdx.x];
+    for (int c = threadIdx.x; c < it.C; c += blockDim.x) {
+        const float m = stats[it.sums_off + c] * it.inv_n;
+        const float var = fmaxf(stats[it.sums_off + it.C + c] * it.inv_n - m * m, 0.f);
+        bn_stats[it.out_off + c] = m + (it.bias_off >= 0 ? params[it.bias_off + c] : 0.f);
+        bn_stats[it.out_off + it.C + c] = var;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
@@ -592,6 +626,8 @@ public:
     BnHost head_bn2, head_bn3;
     long long head_off[8] = {0};      // bn2.w bn2.b bn3.w bn3.b linear1.w linear1.b linear2.w linear2.b
     float* head_scratch = nullptr;
+    BnFinalizeItem* bn_items = nullptr;
+    std::vector<BnFinalizeItem> bn_items_host;
     float *x_keep = nullptr, *mask1_keep = nullptr, *mask2_keep = nullptr, *params_keep = nullptr;   // inputs of the last forward
     HeadScratch hs{};
     float *dl1 = nullptr, *dd1 = nullptr, *dpool = nullptr;
@@ -610,6 +646,7 @@ public:
         if (stats) cudaFree(stats);
         if (head_scratch) cudaFree(head_scratch);
         if (x_keep) cudaFree(x_keep);
+        if (bn_items) cudaFree(bn_items);
     }
 
     // ---- allocation: bf16 chunk-planar planes with zero guards, carved from one zero-initialised workspace
@@ -806,7 +843,8 @@ TrainNet* train_create(int max_batch, int num_sms, const NetConfig& cfg, std::st
     if (n->cursor > n->workspace_bytes) { err = "internal: training workspace under-estimated"; delete n; return nullptr; }
     n->dy_last = n->dlevels[cur];
 
-    if (cudaMalloc(reinterpret_cast<void**>(&n->stats), n->stats_floats * sizeof(float)) != cudaSuccess) { err = "cudaMalloc failed"; delete n; return nullptr; }
+    if (cudaMalloc(reinterpret_cast<void**>(&n->stats), n->stats_floats * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&n->bn_items), 64 * sizeof(BnFinalizeItem)) != cudaSuccess) { err = "cudaMalloc failed"; delete n; return nullptr; }
     {
         const size_t Bm = max_batch;
         const size_t floats = Bm * (3 * kHeadFeat + 3 * kHeadHidden + 1) + kHeadFeat + kHeadHidden + Bm * (kHeadHidden + 2 * kHeadFeat) + 64;
@@ -985,6 +1023,10 @@ namespace {
     } while (0)
 
 inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+// grid of an element-wise grid-stride kernel: enough 256-thread blocks to fill the GPU, no more than the work needs
+inline unsigned ew_grid(const TrainNet* n, long long items) {
+    return static_cast<unsigned>(std::max<long long>(1, std::min<long long>((items + 255) / 256, static_cast<long long>(n->num_sms) * 16)));
+}
 
 cudaError_t run_gemm(TrainNet* n, const GemmLaunch& L, const TPlane& geom, cudaStream_t stream, std::string& err) {
     const long long M = static_cast<long long>(n->B) * geom.hp * geom.wp;
@@ -1081,7 +1123,7 @@ cudaError_t train_forward(TrainNet* n, const float* params, const float* x, int 
         c.bn.count = static_cast<long long>(B) * n->cfg.H * n->cfg.W;
         stem_fwd_kernel<<<blocks_for(c.bn.count, 256), 256, 0, stream>>>(x, B, n->cfg.H, n->cfg.W, params + c.w_off, c.z, n->stats + c.bn.fwd_sums);
         const long long work = c.bn.count * 8;
-        bn_apply_kernel<<<blocks_for(work, 256), 256, 0, stream>>>(c.z, bn_ref(*n, c.bn), 1, 0, c.z, bn_ref(*n, c.bn), n->levels[0], B);
+        bn_apply_kernel<<<ew_grid(n, work), 256, 0, stream>>>(c.z, bn_ref(*n, c.bn), 1, 0, c.z, bn_ref(*n, c.bn), n->levels[0], B);
         n->launches += 2;
     }
     for (auto& blk : n->blocks) {
@@ -1092,15 +1134,15 @@ cudaError_t train_forward(TrainNet* n, const float* params, const float* x, int 
         const TPlane& out = n->levels[blk.out_level];
         c1.bn.count = c2.bn.count = static_cast<long long>(B) * h.H * h.W;
         if (cudaError_t e = run_gemm(n, c1.fwd, c1.z, stream, err)) return e;
-        bn_apply_kernel<<<blocks_for(c1.bn.count * (c1.cout / 8), 256), 256, 0, stream>>>(c1.z, bn_ref(*n, c1.bn), 1, 0, c1.z, bn_ref(*n, c1.bn), h, B);
+        bn_apply_kernel<<<ew_grid(n, c1.bn.count * (c1.cout / 8)), 256, 0, stream>>>(c1.z, bn_ref(*n, c1.bn), 1, 0, c1.z, bn_ref(*n, c1.bn), h, B);
         if (cudaError_t e = run_gemm(n, c2.fwd, c2.z, stream, err)) return e;
         if (blk.sc >= 0) {
             ConvHost& cs = n->convs[blk.sc];
             cs.bn.count = c2.bn.count;
             if (cudaError_t e = run_gemm(n, cs.fwd, cs.z, stream, err)) return e;
-            bn_apply_kernel<<<blocks_for(c2.bn.count * (c2.cout / 8), 256), 256, 0, stream>>>(c2.z, bn_ref(*n, c2.bn), 1, 2, cs.z, bn_ref(*n, cs.bn), out, B);
+            bn_apply_kernel<<<ew_grid(n, c2.bn.count * (c2.cout / 8)), 256, 0, stream>>>(c2.z, bn_ref(*n, c2.bn), 1, 2, cs.z, bn_ref(*n, cs.bn), out, B);
         } else {
-            bn_apply_kernel<<<blocks_for(c2.bn.count * (c2.cout / 8), 256), 256, 0, stream>>>(c2.z, bn_ref(*n, c2.bn), 1, 1, xin, bn_ref(*n, c2.bn), out, B);
+            bn_apply_kernel<<<ew_grid(n, c2.bn.count * (c2.cout / 8)), 256, 0, stream>>>(c2.z, bn_ref(*n, c2.bn), 1, 1, xin, bn_ref(*n, c2.bn), out, B);
         }
         n->launches += 2;
     }
@@ -1111,25 +1153,16 @@ cudaError_t train_forward(TrainNet* n, const float* params, const float* x, int 
                                            bn_stats + head_stat0);
     ++n->launches;
     LD_TRY(cudaGetLastError());
-    // conv BatchNorm statistics (mean, biased variance) for the running-statistics update on the host side
+    // conv BatchNorm statistics (mean incl. conv bias, biased variance) for the caller's running-statistics update
     {
-        std::vector<float> h(n->stats_floats), hp(n->n_params);
-        LD_TRY(cudaMemcpyAsync(h.data(), n->stats, h.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
-        LD_TRY(cudaMemcpyAsync(hp.data(), params, hp.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
-        LD_TRY(cudaStreamSynchronize(stream));
-        std::vector<float> out(n->bn_stats_floats, 0.f);
-        for (const auto& c : n->convs) {
-            const double inv = 1.0 / static_cast<double>(c.bn.count);
-            for (int ch = 0; ch < c.bn.C; ++ch) {
-                const double m = h[c.bn.fwd_sums + ch] * inv;
-                // the kernels leave the conv bias out (it cancels in the normalisation); the BatchNorm's input mean has it
-                out[c.bn.stat_out + ch] = static_cast<float>(m + (c.b_off >= 0 ? hp[c.b_off + ch] : 0.0));
-                out[c.bn.stat_out + c.bn.C + ch] = static_cast<float>(std::max(0.0, h[c.bn.fwd_sums + c.bn.C + ch] * inv - m * m));
-            }
-        }
-        const int conv_floats = head_stat0;   // conv BatchNorms come first in bn_stats
-        LD_TRY(cudaMemcpyAsync(bn_stats, out.data(), conv_floats * sizeof(float), cudaMemcpyHostToDevice, stream));
-        LD_TRY(cudaStreamSynchronize(stream));
+        std::vector<BnFinalizeItem>& items = n->bn_items_host;   // persistent: the async copy may read it after we return
+        items.clear();
+        for (const auto& c : n->convs)
+            items.push_back({c.bn.fwd_sums, c.bn.stat_out, c.bn.C, c.b_off, 1.f / static_cast<float>(c.bn.count)});
+        LD_TRY(cudaMemcpyAsync(n->bn_items, items.data(), items.size() * sizeof(BnFinalizeItem), cudaMemcpyHostToDevice, stream));
+        bn_finalize_kernel<<<static_cast<unsigned>(items.size()), 64, 0, stream>>>(n->bn_items, static_cast<int>(items.size()), n->stats, params, bn_stats);
+        ++n->launches;
+        LD_TRY(cudaGetLastError());
     }
     return cudaSuccess;
 }
@@ -1212,7 +1245,7 @@ cudaError_t train_backward(TrainNet* n, const float* dprobs, float* grads, cudaS
         const long long work = c.bn.count * (c.cout / 8);
         const unsigned grid_r = static_cast<unsigned>(std::min<long long>((work + 255) / 256, n->num_sms * 8));
         bn_bwd_reduce_kernel<<<grid_r, 256, 0, stream>>>(dy, y, relu, c.z, bn_ref(*n, c.bn), B, sums);
-        bn_bwd_apply_kernel<<<blocks_for(work, 256), 256, 0, stream>>>(dy, y, relu, c.z, bn_ref(*n, c.bn), sums, B, c.dz, write_g, g_out,
+        bn_bwd_apply_kernel<<<ew_grid(n, work), 256, 0, stream>>>(dy, y, relu, c.z, bn_ref(*n, c.bn), sums, B, c.dz, write_g, g_out,
                                                                       grads + c.bn.gamma_off, grads + c.bn.beta_off);
         n->launches += 2;
     };
