@@ -75,7 +75,7 @@ def main():
     l_lines, l_json = launch_list(tag)
     f_lines, names, traffic = full_capture()
     with open(os.path.join(dst, "ncu_summary.md"), "w") as f:
-        f.write(f"# ncu summary ({tag})\n\nCommand: `python bench.py --channels 1 --minutes 10 --steps 1 --warmup 1 --no-cpu-baseline` "
+        f.write(f"# ncu summary ({tag})\n\nCommand: `python bench.py --channels 1 --minutes 10 --steps 1 --warmup 1 --no-cpu-baseline --train-steps 0` "
                 "(one 10-minute channel = 60 000 windows, 2 chunks x 19 conv launches per pass).\n\n"
                 "## Launch list (`--metrics gpu__time_duration.sum --clock-control none`, cold-cache, serialised: compare SHARES)\n\n")
         f.write("\n".join(l_lines) + "\n\n## Full capture of the block1 conv launches (`--set full`, launches = block1.0.conv1, "
