@@ -143,7 +143,7 @@ def time_training(local_rank, world, batch, steps, warmup):
     model = models.ResNetBigger(dropout_rate=0.5, linear_layer_size=48, filter_sizes=[64, 32, 16, 16])
     model.load_state_dict(synth.synthetic_state_dict(head_gain=1.0, head_bias_shift=0.0))
     model.set_device(dev)
-    opt = torch.optim.Adam(model.parameters())
+    opt = ld_train.B200Adam(model)   # K8: clip_grad_norm_(1.0) + Adam fused on the flat parameter vector
     rank = int(os.environ.get("RANK", "0"))
     batches = []
     for s in range(4):
@@ -151,12 +151,12 @@ def time_training(local_rank, world, batch, steps, warmup):
         batches.append({k: v.pin_memory() for k, v in b.items()})
     loss = 0.0
     for i in range(warmup):
-        loss = ld_train.train_batch(model, opt, batches[i % 4], dev, world_size=world)[0]
+        loss = ld_train.train_batch_fused(model, opt, batches[i % 4], dev, world_size=world)[0]
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        loss = ld_train.train_batch(model, opt, batches[i % 4], dev, world_size=world)[0]
+        loss = ld_train.train_batch_fused(model, opt, batches[i % 4], dev, world_size=world)[0]
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / steps, loss
@@ -297,7 +297,7 @@ def run_b200(args):
                 (train_ms_max * 1e-3), "unit": "samples/sec", "ms_per_step": train_ms_max, "batch_per_gpu": args.train_batch,
                 "steps": args.train_steps, "last_loss": train_loss, "scaling": "weak",
                 "includes": "H2D of the batch from pinned host memory, forward, backward, flat-bucket gradient all-reduce (N>1), "
-                            "clip_grad_norm_ 1.0, Adam", "data": "synthetic LAD windows (100 x 44 log-mel-like), labels recoverable"}
+                            "fused clip_grad_norm_ 1.0 + Adam (ld_clip_adam_step), per-step loss/accuracy read-back like train.py:297", "data": "synthetic LAD windows (100 x 44 log-mel-like), labels recoverable"}
         if n_gpus == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
             v, dt = time_cpu_reference(args.cpu_sample_seconds, 1, 1)

@@ -143,6 +143,12 @@ LD_API int ld_train_forward(ld_ctx* ctx, const float* params_d, const float* x_d
                      const float* mask2_d, float dropout_p, float* probs_d, float* bn_stats_d, void* stream);
 LD_API int ld_train_backward(ld_ctx* ctx, const float* dprobs_d, float* grads_d, void* stream);
 LD_API int64_t ld_train_kernel_launches(const ld_ctx* ctx);
+/* K8. Replaces torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm) + optimizer.step() of train.py:292-295 with
+ * optim.Adam (train.py:336; PyTorch's update arithmetic) on flat fp32 device vectors of n elements: params updated in place,
+ * exp_avg / exp_avg_sq are Adam's state, `step` counts from 1.  max_norm <= 0 disables clipping.  grad_norm_d (optional,
+ * device) receives the un-clipped global L2 norm.  For data-parallel training all-reduce grads_d before the call. */
+LD_API int ld_clip_adam_step(ld_ctx* ctx, float* params_d, const float* grads_d, float* exp_avg_d, float* exp_avg_sq_d, int64_t n,
+                      float max_norm, float lr, float beta1, float beta2, float eps, int64_t step, float* grad_norm_d, void* stream);
 /* Debug: sum |value| of every conv output, activation, conv-output gradient and input-gradient plane of the last step. */
 LD_API int32_t ld_train_debug_checksums(ld_ctx* ctx, double* out, int32_t cap);
 /* Debug: one tensor of the last training step as dense (B, C, H, W) fp32 in host memory.  kind 0: conv output z of conv

@@ -796,6 +796,18 @@ int32_t ld_train_debug_checksums(ld_ctx* ctx, double* out, int32_t cap) {
     return ld::train_debug_checksums(ctx->train, out, cap);
 }
 
+int ld_clip_adam_step(ld_ctx* ctx, float* params_d, const float* grads_d, float* exp_avg_d, float* exp_avg_sq_d, int64_t n, float max_norm,
+                      float lr, float beta1, float beta2, float eps, int64_t step, float* grad_norm_d, void* stream_v) {
+    if (!ctx || !params_d || !grads_d || !exp_avg_d || !exp_avg_sq_d || n <= 0 || step < 1) return fail(LD_ERR_INVALID, "bad arguments");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (int r = ctx->thr_buf.ensure(64)) return r;
+    float* scratch = static_cast<float*>(ctx->thr_buf.p);
+    LD_CUDA(ld::clip_adam_step(params_d, grads_d, exp_avg_d, exp_avg_sq_d, n, max_norm, lr, beta1, beta2, eps, step, scratch, stream));
+    if (grad_norm_d) LD_CUDA(cudaMemcpyAsync(grad_norm_d, scratch + 1, sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    return LD_OK;
+}
+
 int64_t ld_train_debug_read(ld_ctx* ctx, int32_t kind, int32_t index, float* out_host, int32_t* dims4) {
     if (!ctx || !ctx->train) { fail(LD_ERR_STATE, "ld_train_create has not been called"); return -1; }
     cudaSetDevice(ctx->device);

@@ -1227,6 +1227,56 @@ long long train_debug_read(TrainNet* n, int kind, int index, float* out, int* di
     return total;
 }
 
+// ------------------------------------------------------------------------------------------------ K8: clip + Adam
+// torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam(...).step() (train.py:292-295,336) on ONE flat
+// fp32 parameter / gradient vector: pass 1 = global sum of squares, pass 2 = scale by min(1, max_norm / (norm + 1e-6)) and the
+// Adam update with PyTorch's bias-correction arithmetic.
+namespace {
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+    float acc = 0.f;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        acc = fmaf(g[i], g[i], acc);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ float s_part[8];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += s_part[i];
+        atomicAdd(out, t);
+    }
+}
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                 const float* __restrict__ sumsq, float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
+                 float* __restrict__ norm_out) {
+    const float norm = sqrtf(*sumsq);
+    const float scale = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
+    if (norm_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = norm;
+    const float step_size = lr / bc1;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float gi = g[i] * scale;
+        const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+        const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+        m[i] = mi; v[i] = vi;
+        p[i] -= step_size * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    }
+}
+}  // namespace
+
+cudaError_t clip_adam_step(float* params, const float* grads, float* m, float* v, long long n, float max_norm, float lr, float b1,
+                           float b2, float eps, long long step, float* scratch2, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(scratch2, 0, sizeof(float), stream);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = static_cast<unsigned>(std::max<long long>(1, std::min<long long>((n + 255) / 256, 592)));
+    sumsq_kernel<<<grid, 256, 0, stream>>>(grads, n, scratch2);
+    const float bc1 = 1.f - std::pow(b1, static_cast<float>(step));
+    const float bc2 = 1.f - std::pow(b2, static_cast<float>(step));
+    clip_adam_kernel<<<grid, 256, 0, stream>>>(params, grads, m, v, n, scratch2, max_norm, lr, b1, b2, eps, bc1, std::sqrt(bc2), scratch2 + 1);
+    return cudaGetLastError();
+}
+
 cudaError_t train_backward(TrainNet* n, const float* dprobs, float* grads, cudaStream_t stream, std::string& err) {
     if (n->B <= 0 || n->params_d == nullptr) { err = "train_backward without a preceding train_forward"; return cudaErrorInvalidValue; }
     const int B = n->B;

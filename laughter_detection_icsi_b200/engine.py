@@ -273,6 +273,17 @@ class Engine:
             check(self.lib.ld_train_backward(self._h, dprobs.data_ptr(), grads.data_ptr(), self._stream()))
         return grads
 
+    def clip_adam_step(self, params, grads, exp_avg, exp_avg_sq, step, max_norm=1.0, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                       grad_norm_out=None):
+        """K8: clip_grad_norm_(max_norm) + Adam step on flat fp32 CUDA vectors, in place (ld_clip_adam_step)."""
+        for t in (params, grads, exp_avg, exp_avg_sq):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == params.numel()):
+                raise ValueError("clip_adam_step needs contiguous float32 CUDA vectors of equal length")
+        with torch.cuda.device(self.device):
+            check(self.lib.ld_clip_adam_step(self._h, params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                             params.numel(), float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                             int(step), grad_norm_out.data_ptr() if grad_norm_out is not None else None, self._stream()))
+
     def train_debug_read(self, kind, index):
         """Dense (B, C, H, W) float32 numpy copy of one training tensor (see ld_train_debug_read)."""
         dims = (ctypes.c_int32 * 4)()

@@ -114,6 +114,35 @@ class ResNetBigger(nn.Module):
                 raise LdError("parameter order of the module and of the CUDA training network disagree")
         return eng
 
+    # ---- flat parameter storage: one fp32 vector whose slices ARE the parameters (views), so the training kernels read it
+    #      directly and the fused optimiser (train.B200Adam / ld_clip_adam_step) updates every parameter in one launch
+    def flatten_parameters(self):
+        params = list(self.parameters())
+        flat = getattr(self, "_ld_flat", None)
+        if flat is not None and flat.device == params[0].device and all(
+                q.data_ptr() == flat.data_ptr() + 4 * off for q, off in zip(params, self._ld_flat_offsets)):
+            return flat
+        flat = torch.cat([q.detach().reshape(-1).float() for q in params]).contiguous()
+        offsets, off = [], 0
+        for q in params:
+            n = q.numel()
+            q.data = flat[off:off + n].view_as(q)
+            offsets.append(off)
+            off += n
+        self._ld_flat, self._ld_flat_offsets = flat, offsets
+        self._ld_flat_leaves = []
+        return flat
+
+    def flat_gradient(self):
+        """The flat gradient accumulated since the last zero (same layout as flatten_parameters()), or None."""
+        grads = [l.grad for l in (getattr(self, "_ld_flat_leaves", None) or []) if l.grad is not None]
+        if not grads:
+            return None
+        return grads[0] if len(grads) == 1 else torch.stack(grads).sum(0)
+
+    def zero_flat_gradient(self):
+        self._ld_flat_leaves = []
+
     def _forward_train(self, x):
         """Training-mode forward on the B200 kernels (batch-statistics BatchNorm, dropout); autograd-connected to
         the module parameters through one flat parameter vector, so loss.backward() fills .grad like the reference."""
@@ -128,9 +157,16 @@ class ResNetBigger(nn.Module):
             mask1 = torch.ones(B, self.linear_layer_size, device=dev)
             mask2 = torch.ones(B, 32, device=dev)
         self._ld_last_masks = (mask1, mask2)
-        flat = torch.cat([q.reshape(-1) for q in self.parameters()])
         feats = x.detach().float().reshape(B, x.shape[2], x.shape[3]).contiguous()
-        probs, bn_stats = _TrainFunction.apply(flat, feats, mask1, mask2, p, eng)
+        if getattr(self, "_ld_fused", False):
+            # fused-optimiser mode (train.B200Adam): the flat vector is the leaf; its gradient stays flat
+            leaf = self.flatten_parameters().detach().requires_grad_(True)   # shares storage; its .grad is the flat gradient
+            self._ld_flat_leaves = getattr(self, "_ld_flat_leaves", None) or []
+            self._ld_flat_leaves.append(leaf)
+            probs, bn_stats = _TrainFunction.apply(leaf, feats, mask1, mask2, p, eng)
+        else:
+            flat = torch.cat([q.reshape(-1) for q in self.parameters()])
+            probs, bn_stats = _TrainFunction.apply(flat, feats, mask1, mask2, p, eng)
         self._update_running_stats(eng, bn_stats, B)
         return probs.reshape(B, 1)
 

@@ -51,6 +51,60 @@ def train_batch(model, optimizer, batch, device, clip=1.0, gradient_accumulation
     return float(loss.detach()), acc, prec, recall
 
 
+class B200Adam:
+    """Fused clip_grad_norm_(max_norm) + Adam (train.py:292-295,336) for a ResNetBigger with flat parameter storage: ONE kernel
+    pair (global norm, update) on the flat fp32 vector (ld_clip_adam_step, K8) instead of ~190 small PyTorch launches.
+    Same arithmetic as torch.optim.Adam with default hyper-parameters; data parallel: pass world_size > 1 and the flat
+    gradient is all-reduced (mean) first."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
+        self.model, self.lr, self.betas, self.eps, self.max_norm = model, lr, betas, eps, max_norm
+        flat = model.flatten_parameters()
+        model._ld_fused = True
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(flat), torch.zeros_like(flat)
+        self.grad_norm = torch.zeros(1, device=flat.device)
+        self.steps = 0
+
+    def zero_grad(self):
+        self.model.zero_flat_gradient()
+
+    def step(self, world_size=1):
+        import torch.distributed as dist
+        g = self.model.flat_gradient()
+        if g is None:
+            raise RuntimeError("B200Adam.step() without a backward pass")
+        g = g.contiguous()
+        if world_size > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            g.div_(world_size)
+        self.steps += 1
+        eng = self.model._train_engine(1)
+        eng.clip_adam_step(self.model.flatten_parameters(), g, self.exp_avg, self.exp_avg_sq, self.steps, self.max_norm, self.lr,
+                           self.betas, self.eps, self.grad_norm)
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "steps": self.steps}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"]); self.steps = int(sd["steps"])
+
+
+def train_batch_fused(model, optimizer, batch, device, world_size=1, sync_metrics=True):
+    """train_batch with the fused optimiser: forward, BCELoss, backward, (all-reduce,) clip + Adam in one kernel pair."""
+    model.train()
+    segs = batch['inputs'][:, None, :, :].to(device, non_blocking=True)
+    labs = batch['is_laugh'].float().to(device, non_blocking=True)
+    optimizer.zero_grad()
+    output = model(segs).squeeze()
+    loss = nn.BCELoss()(output, labs)
+    loss.backward()
+    optimizer.step(world_size)
+    if not sync_metrics:
+        return loss.detach(), None, None, None
+    acc, prec, recall = _calc_metrics(output.detach(), labs)
+    return float(loss.detach()), acc, prec, recall
+
+
 def synthetic_lad_batch(batch_size, seed, device="cpu"):
     """LadDataset-shaped batch ({'inputs': (B,100,44) float32, 'is_laugh': (B,) int32}) of log-mel-like windows whose
     label is recoverable (laugh windows carry a 5 Hz harmonic modulation), SURVEY.md section 8d config 4."""
