@@ -29,6 +29,9 @@ __device__ __forceinline__ int find_channel(const ChannelTable& ct, long long s,
     return (local >= 0 && local < ct.frames[lo]) ? lo : -1;
 }
 
+// One thread computes kStemPx consecutive pixels of a row for all 64 channels: every weight fetched from shared memory is
+// used kStemPx times (the one-pixel version was bound by its 576 shared-memory loads per pixel).
+constexpr int kStemPx = 4;
 __global__ void __launch_bounds__(256)
 stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long long chunk_row0, int rows) {
     __shared__ float s_w[64 * 9];
@@ -39,18 +42,14 @@ stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long
 
     const StemJob job = L.jobs[blockIdx.y];
     const int wp = L.W + 2;
-    const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (p >= static_cast<long long>(rows) * wp) return;
-    const long long r = p / wp;
-    const int col = static_cast<int>(p - r * wp) - 1;  // real column, -1 and W are padding
-    __half* out = job.out + p * 8;
+    const int groups_per_row = (wp + kStemPx - 1) / kStemPx;
+    const long long gi = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gi >= static_cast<long long>(rows) * groups_per_row) return;
+    const long long r = gi / groups_per_row;
+    const int pc0 = static_cast<int>(gi - r * groups_per_row) * kStemPx;   // first padded column of this thread
 
-    if (col < 0 || col >= L.W) {
-        const uint4 z = make_uint4(0, 0, 0, 0);
-        for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(out + kc * job.kc_stride) = z;
-        return;
-    }
-    float x[9];
+    // the 3 x (kStemPx + 2) input patch; real column = padded column - 1
+    float x[3][kStemPx + 2];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         long long local = 0;
@@ -58,28 +57,41 @@ stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long
         const int c = ((job.mask >> ky) & 1) ? find_channel(ct, s, local) : -1;
         const float* frow = (c >= 0) ? feats + (ct.feat_off[c] + local) * L.W : nullptr;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int cc = col + kx - 1;
-            x[ky * 3 + kx] = (frow != nullptr && cc >= 0 && cc < L.W) ? __ldg(frow + cc) : 0.f;
+        for (int k = 0; k < kStemPx + 2; ++k) {
+            const int cc = pc0 - 1 + k - 1;
+            x[ky][k] = (frow != nullptr && cc >= 0 && cc < L.W) ? __ldg(frow + cc) : 0.f;
         }
     }
+    float acc[kStemPx][8];
     for (int kc = 0; kc < 8; ++kc) {
-        uint4 ov;
-        __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float a[2];
+        for (int e = 0; e < 8; ++e) {
+            const int ch = kc * 8 + e;
+            float w[9];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int ch = kc * 8 + 2 * e + h;
-                float acc = 0.f;
+            for (int t = 0; t < 9; ++t) w[t] = s_w[ch * 9 + t];
+            const float sc = s_scale[ch], sh = s_shift[ch];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) acc = fmaf(s_w[ch * 9 + t], x[t], acc);
-                a[h] = fmaxf(fmaf(acc, s_scale[ch], s_shift[ch]), 0.f);
+            for (int px = 0; px < kStemPx; ++px) {
+                float a = 0.f;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) a = fmaf(w[ky * 3 + kx], x[ky][px + kx], a);
+                acc[px][e] = fmaxf(fmaf(a, sc, sh), 0.f);
             }
-            oh[e] = __floats2half2_rn(a[0], a[1]);
         }
-        *reinterpret_cast<uint4*>(out + kc * job.kc_stride) = ov;
+#pragma unroll
+        for (int px = 0; px < kStemPx; ++px) {
+            const int pc = pc0 + px;
+            if (pc >= wp) continue;
+            uint4 ov;
+            __half2* oh = reinterpret_cast<__half2*>(&ov);
+            const bool pad = pc == 0 || pc == wp - 1;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) oh[e] = pad ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(acc[px][2 * e], acc[px][2 * e + 1]);
+            *reinterpret_cast<uint4*>(job.out + (r * wp + pc) * 8 + kc * job.kc_stride) = ov;
+        }
     }
 }
 
@@ -143,8 +155,8 @@ head_kernel(HeadLaunch L, ChannelTable ct, float* __restrict__ probs, long long 
 
 cudaError_t launch_stem(const StemLaunch& L, const ChannelTable& ct, const float* feats, long long chunk_row0,
                         int rows, cudaStream_t stream) {
-    const long long pixels = static_cast<long long>(rows) * (L.W + 2);
-    dim3 grid(static_cast<unsigned>((pixels + 255) / 256), L.n_jobs);
+    const long long groups = static_cast<long long>(rows) * ((L.W + 2 + kStemPx - 1) / kStemPx);
+    dim3 grid(static_cast<unsigned>((groups + 255) / 256), L.n_jobs);
     stem_kernel<<<grid, 256, 0, stream>>>(L, ct, feats, chunk_row0, rows);
     return cudaGetLastError();
 }

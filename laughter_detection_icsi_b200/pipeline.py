@@ -56,9 +56,34 @@ class LaughterPipeline:
         return out
 
     def __call__(self, pcm_host, chan_len, durations_s=None):
-        """pcm_host: int16 host tensor (pinned for full copy bandwidth). Returns (per-channel instance dicts, frames)."""
-        pcm_dev = pcm_host.to(self.engine.device, non_blocking=True)
-        runs, frames = self.step_device(pcm_dev, chan_len)
+        """pcm_host: int16 host tensor (pinned for full copy bandwidth). Returns (per-channel instance dicts, frames).
+        The channels are copied on a side stream one by one and the network starts on channel c as soon as it has
+        landed, so all but the first channel's H2D copy overlaps with compute."""
+        dev = self.engine.device
+        chan_len = [int(n) for n in chan_len]
+        pcm_host = pcm_host.reshape(-1)
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        pcm_dev = torch.empty(pcm_host.numel(), dtype=torch.int16, device=dev)
+        self._copy_stream.wait_stream(main)   # the destination was allocated on the main stream
+        events, off = [], 0
+        with torch.cuda.stream(self._copy_stream):
+            for n in chan_len:
+                pcm_dev[off:off + n].copy_(pcm_host[off:off + n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                events.append(ev)
+                off += n
+        probs, frames, off = [], [], 0
+        for n, ev in zip(chan_len, events):
+            main.wait_event(ev)
+            p, f = self.probabilities(pcm_dev[off:off + n], [n])
+            probs.append(p)
+            frames += f
+            off += n
+        pcm_dev.record_stream(self._copy_stream)
+        runs = self.runs(torch.cat(probs) if len(probs) > 1 else probs[0], frames)
         if durations_s is None:
             durations_s = [n / float(_engine.SAMPLE_RATE) for n in chan_len]
         return self.instances(runs, frames, durations_s), frames
