@@ -43,6 +43,14 @@ def create_training_dataloader(cutset_dir, split, shuffle=False):
     if split not in ['train', 'dev', 'test']:
         raise ValueError(
             f"Unexpected value for split. Needs to be one of 'train, dev, test'. Found {split}")
+    store_manifest = os.path.join(cutset_dir, 'feats.jsonl')
+    split_df = os.path.join(cutset_dir, f'{split}_df.csv')
+    if os.path.exists(store_manifest) and os.path.exists(split_df):
+        # lhotse-free path: raw GPU feature store + data frame (compute_features.FeatureStore)
+        from . import compute_features as cf
+        store = cf.FeatureStore.load(cutset_dir)
+        cuts = cf.cuts_from_dataframe(cf.read_data_df(split_df), store, shuffle_seed=0 if shuffle else None)
+        return list(cf.training_batches(cuts, max_cuts=32))
     try:
         from lhotse import CutSet
         from lhotse.dataset import SingleCutSampler

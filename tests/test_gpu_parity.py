@@ -345,3 +345,27 @@ def test_segment_laughter_cli_end_to_end(tmp_path):
     with pytest.raises(Exception, match="Model checkpoint not found"):
         segment_laughter.main(["--config", "resnet_base", "--model_path", str(tmp_path / "nope"), "--input_audio_file", str(wav),
                                "--output_dir", str(out)])
+
+
+def test_feature_store_from_wav_feeds_training(tmp_path):
+    """whole-track features from K1 -> LAD cuts from a data frame -> LadDataset batch ->
+    one training step on the B200 kernels."""
+    import scipy.io.wavfile
+    from laughter_detection_icsi_b200 import compute_features as cf, train as ld_train
+    pcm = synth.synth_channel(16000 * 20, meeting=7, channel=1).numpy()
+    wav = tmp_path / "chan1.wav"
+    scipy.io.wavfile.write(str(wav), 16000, pcm)
+    store = cf.FeatureStore()
+    store.add_track("Bmr007", "chan1", str(wav))
+    ref = fbank_oracle.fbank(pcm.astype(np.float64) / 32768.0, dtype=torch.float64).numpy()
+    assert feat_err(store.tracks["Bmr007/chan1"], ref) < FEAT_RTOL
+    rows = [{"meeting_id": "Bmr007", "chan_id": "chan1", "sub_start": 0.5 * i, "sub_duration": 1.0 if i % 3 else 0.4, "label": i % 2}
+            for i in range(32)]
+    cuts = cf.cuts_from_dataframe(rows, store)
+    assert feat_err(cuts[1].load_features(), ref[50:150]) < FEAT_RTOL
+    batch = next(cf.training_batches(cuts))
+    m = models.ResNetBigger(dropout_rate=0.5, linear_layer_size=48, filter_sizes=[64, 32, 16, 16])
+    m.load_state_dict(synth.synthetic_state_dict(head_gain=1.0, head_bias_shift=0.0))
+    m.set_device("cuda")
+    loss = ld_train.train_batch(m, torch.optim.Adam(m.parameters()), batch, torch.device("cuda"))[0]
+    assert np.isfinite(loss)

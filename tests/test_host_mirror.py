@@ -140,3 +140,32 @@ def test_synthetic_audio_is_reproducible():
     b = synth.synth_channel(16000, meeting=2, channel=1)
     c = synth.synth_channel(16000, meeting=2, channel=2)
     assert a.dtype == torch.int16 and torch.equal(a, b) and not torch.equal(a, c)
+
+
+def test_feature_store_cuts_follow_truncate_and_pad(tmp_path):
+    from laughter_detection_icsi_b200 import compute_features as cf
+    store = cf.FeatureStore()
+    feats = np.arange(3000 * 44, dtype=np.float32).reshape(3000, 44)
+    store.add_features("Bmr021", "chan3", feats, "Bmr021/chan3.sph", 30.0)
+    c = store.cut("Bmr021", "chan3", sub_start=14.785, sub_duration=1.0, label=0)          # 1478.5 -> frame 1479 (half up)
+    assert c.load_features().shape == (100, 44) and np.array_equal(c.load_features(), feats[1479:1579])
+    short = store.cut("Bmr021", "chan3", sub_start=2.0, sub_duration=0.37, label=1)         # 37 frames + 63 pad frames
+    w = short.load_features()
+    assert np.array_equal(w[:37], feats[200:237]) and np.all(w[37:] == np.float32(cf.LOG_EPSILON)) and short.supervisions[0].custom["is_laugh"] == 1
+    tail = store.cut("Bmr021", "chan3", sub_start=29.5, sub_duration=1.0, label=0)          # runs off the end of the track
+    assert np.array_equal(tail.load_features()[:50], feats[2950:]) and np.all(tail.load_features()[50:] == np.float32(cf.LOG_EPSILON))
+    # data-frame rows in the reference's sample_df.csv format -> shuffled cuts -> LadDataset batches of 32
+    csv_path = tmp_path / "train_df.csv"
+    csv_path.write_text("start,duration,sub_start,sub_duration,audio_path,meeting_id,chan_id,label\n" +
+                        "".join(f"{i}.0,1.5,{i}.25,1.0,Bmr021/chan3.sph,Bmr021,chan3,{i % 2}\n" for i in range(1, 28)) +
+                        "".join(f"{i}.0,0.5,{i}.1,0.5,Bmr021/chan3.sph,Bmr021,chan3,1\n" for i in range(1, 14)))
+    rows = cf.read_data_df(str(csv_path))
+    cuts = cf.cuts_from_dataframe(rows, store, shuffle_seed=0)
+    assert len(cuts) == 40 and sorted(c.id for c in cuts) == sorted(f"cut_{i}" for i in range(40))
+    batches = list(cf.training_batches(cuts))
+    assert [b["inputs"].shape[0] for b in batches] == [32, 8] and batches[0]["inputs"].shape[1:] == (100, 44)
+    assert batches[0]["is_laugh"].dtype == torch.int32
+    # save / load round trip of the raw store format
+    store.save(str(tmp_path / "store"))
+    again = cf.FeatureStore.load(str(tmp_path / "store"))
+    assert np.array_equal(again.tracks["Bmr021/chan3"], feats) and again.meta["Bmr021/chan3"]["num_frames"] == 3000
