@@ -1,17 +1,61 @@
-"""Mirror of the reference's utils/audio_utils.py:7-9 (duration via audioread) for WAV files, plus the PCM
-loader the inference path needs (lhotse ``Recording.from_file`` / ``load_audio`` in load_data.py:44-45)."""
+"""Mirror of the reference's utils/audio_utils.py:7-9 (duration via audioread), plus the PCM loader the inference path needs
+(lhotse ``Recording.from_file`` / ``load_audio`` in load_data.py:44-45): 16-bit PCM WAV and NIST SPHERE files with
+uncompressed PCM.  ICSI ships its channels as shorten-compressed SPHERE (``sample_coding pcm,embedded-shorten-v2.00``);
+those must be unpacked first (``sph2pipe -f wav``), as the reference's own helpers do
+(analysis/output_processing/laughs_to_wav.py:95-96)."""
 import wave
 
 import numpy as np
 
 
+def _sphere_header(path):
+    with open(path, "rb") as f:
+        magic = f.readline().strip()
+        if magic != b"NIST_1A":
+            return None
+        size = int(f.readline().strip())
+        f.seek(0)
+        text = f.read(size).decode("latin-1")
+    fields = {}
+    for line in text.split("\n")[2:]:
+        parts = line.strip().split(None, 2)
+        if not parts or parts[0] == "end_head":
+            break
+        if len(parts) == 3:
+            fields[parts[0]] = int(parts[2]) if parts[1] == "-i" else parts[2]
+    fields["_header_bytes"] = size
+    return fields
+
+
+def _load_sphere_int16(path, h):
+    coding = str(h.get("sample_coding", "pcm"))
+    if coding != "pcm":
+        raise ValueError(f"{path}: SPHERE sample_coding '{coding}' is compressed; unpack it first (sph2pipe -f wav)")
+    if int(h.get("sample_n_bytes", 2)) != 2:
+        raise ValueError(f"{path}: only 16-bit PCM SPHERE is supported")
+    dtype = ">i2" if str(h.get("sample_byte_format", "01")) == "10" else "<i2"
+    ch = int(h.get("channel_count", 1))
+    data = np.fromfile(path, dtype=dtype, offset=h["_header_bytes"], count=int(h["sample_count"]) * ch if "sample_count" in h else -1)
+    if ch > 1:
+        data = data.reshape(-1, ch)[:, 0]
+    return np.ascontiguousarray(data.astype(np.int16)), int(h["sample_rate"])
+
+
 def get_audio_length(path):
+    h = _sphere_header(path)
+    if h is not None:
+        return _load_sphere_int16(path, h)[0].shape[0] / float(h["sample_rate"]) if "sample_count" not in h \
+            else int(h["sample_count"]) / float(h["sample_rate"])
     with wave.open(path, "rb") as f:
         return f.getnframes() / float(f.getframerate())
 
 
 def load_wav_int16(path):
-    """Mono 16-bit PCM WAV -> (int16 samples, sampling_rate); multi-channel files use channel 0 (MonoCut channel=0)."""
+    """Mono 16-bit PCM WAV (or uncompressed SPHERE) -> (int16 samples, sampling_rate); multi-channel files use channel 0
+    (MonoCut channel=0)."""
+    h = _sphere_header(path)
+    if h is not None:
+        return _load_sphere_int16(path, h)
     with wave.open(path, "rb") as f:
         if f.getsampwidth() != 2:
             raise ValueError(f"{path}: only 16-bit PCM WAV is supported")

@@ -169,3 +169,26 @@ def test_feature_store_cuts_follow_truncate_and_pad(tmp_path):
     store.save(str(tmp_path / "store"))
     again = cf.FeatureStore.load(str(tmp_path / "store"))
     assert np.array_equal(again.tracks["Bmr021/chan3"], feats) and again.meta["Bmr021/chan3"]["num_frames"] == 3000
+
+
+def test_sphere_pcm_ingest(tmp_path):
+    """NIST SPHERE with uncompressed 16-bit PCM (what sph2pipe-unpacked ICSI channels look like), both byte orders; the
+    shorten-compressed original is refused with a clear message."""
+    pcm = synth.synth_channel(16000 + 7).numpy()
+
+    def write(path, coding, byte_format, data):
+        head = ("NIST_1A\n   1024\nsample_count -i %d\nsample_rate -i 16000\nchannel_count -i 1\nsample_n_bytes -i 2\n"
+                "sample_byte_format -s2 %s\nsample_coding -s%d %s\nend_head\n" % (len(pcm), byte_format, len(coding), coding)).encode()
+        with open(path, "wb") as f:
+            f.write(head + b" " * (1024 - len(head)))
+            f.write(data)
+    le, be, shn = str(tmp_path / "le.sph"), str(tmp_path / "be.sph"), str(tmp_path / "shn.sph")
+    write(le, "pcm", "01", pcm.astype("<i2").tobytes())
+    write(be, "pcm", "10", pcm.astype(">i2").tobytes())
+    write(shn, "pcm,embedded-shorten-v2.00", "01", b"\\x00" * 100)
+    for p in (le, be):
+        got, sr = audio_utils.load_wav_int16(p)
+        assert sr == 16000 and got.dtype == np.int16 and np.array_equal(got, pcm)
+        assert audio_utils.get_audio_length(p) == len(pcm) / 16000.0
+    with pytest.raises(ValueError, match="sph2pipe"):
+        audio_utils.load_wav_int16(shn)
