@@ -49,10 +49,15 @@ class LaughterPipeline:
         for (starts, ends, chans), thr in zip(runs, self.thresholds):
             bounds = np.searchsorted(chans, np.arange(len(frames) + 1))
             for c in range(len(frames)):
-                s, e = starts[bounds[c]:bounds[c + 1]], ends[bounds[c]:bounds[c + 1]]
+                # float64 frame / fps and the strict `end - start > min_len` (laugh_segmenter.py:23-24,108): IEEE double
+                # division and subtraction, element-wise -- the same arithmetic as ld_filter_min_length, done once per
+                # (threshold, channel) and masked per min_length
+                s = starts[bounds[c]:bounds[c + 1]].astype(np.float64) / fps[c]
+                e = ends[bounds[c]:bounds[c + 1]].astype(np.float64) / fps[c]
+                d = e - s
+                se = np.stack([s, e], axis=1)
                 for ml in self.min_lengths:
-                    a, b = self.engine.filter_min_length(s, e, fps[c], ml)
-                    out[c][(thr, ml)] = np.stack([a, b], axis=1)
+                    out[c][(thr, ml)] = se[d > ml]
         return out
 
     def __call__(self, pcm_host, chan_len, durations_s=None):

@@ -89,3 +89,21 @@ def test_compute_entry_points_fail_loudly_without_gpu():
     from laughter_detection_icsi_b200.engine import Engine
     with pytest.raises(_native.LdError):
         Engine(0)
+
+
+def test_numpy_float64_filter_is_the_c_helper():
+    """pipeline.instances vectorises the min-length filter in NumPy float64; it must agree bit for bit with
+    ld_filter_min_length (and through it with the reference's Python floats, see the segmenter golden cases)."""
+    lib = _native.load_library()
+    rng = np.random.default_rng(0)
+    I32, F64 = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)
+    for fps in (100.0, 99.98766, 100.0123, 360000 / 3600.00123):
+        s = rng.integers(0, 300000, 5000).astype(np.int32)
+        e = (s + rng.integers(0, 40, 5000)).astype(np.int32)
+        for ml in (0.0, 0.1, 0.2):
+            os_, oe = np.empty(len(s)), np.empty(len(s))
+            k = lib.ld_filter_min_length(s.ctypes.data_as(I32), e.ctypes.data_as(I32), len(s), fps, ml, os_.ctypes.data_as(F64),
+                                         oe.ctypes.data_as(F64))
+            ss, ee = s.astype(np.float64) / fps, e.astype(np.float64) / fps
+            m = (ee - ss) > ml
+            assert k == m.sum() and np.array_equal(os_[:k], ss[m]) and np.array_equal(oe[:k], ee[m])
