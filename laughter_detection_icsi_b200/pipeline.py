@@ -46,18 +46,38 @@ class LaughterPipeline:
         channel; rows compare equal to the reference's list of tuples (``.tolist()``)."""
         out = [dict() for _ in frames]
         fps = [frames[c] / float(durations_s[c]) for c in range(len(frames))]
+        min_lengths = self.min_lengths
+
+        def one(args):
+            # float64 frame / fps and the strict `end - start > min_len` (laugh_segmenter.py:23-24,108): IEEE double
+            # division and subtraction, element-wise -- the same arithmetic as ld_filter_min_length, done once per
+            # (threshold, channel) and masked per min_length
+            starts, ends, c = args
+            s = starts.astype(np.float64) / fps[c]
+            e = ends.astype(np.float64) / fps[c]
+            d = e - s
+            se = np.stack([s, e], axis=1)
+            return [se[d > ml] for ml in min_lengths]
+
+        work, keys = [], []
         for (starts, ends, chans), thr in zip(runs, self.thresholds):
             bounds = np.searchsorted(chans, np.arange(len(frames) + 1))
             for c in range(len(frames)):
-                # float64 frame / fps and the strict `end - start > min_len` (laugh_segmenter.py:23-24,108): IEEE double
-                # division and subtraction, element-wise -- the same arithmetic as ld_filter_min_length, done once per
-                # (threshold, channel) and masked per min_length
-                s = starts[bounds[c]:bounds[c + 1]].astype(np.float64) / fps[c]
-                e = ends[bounds[c]:bounds[c + 1]].astype(np.float64) / fps[c]
-                d = e - s
-                se = np.stack([s, e], axis=1)
-                for ml in self.min_lengths:
-                    out[c][(thr, ml)] = se[d > ml]
+                work.append((starts[bounds[c]:bounds[c + 1]], ends[bounds[c]:bounds[c + 1]], c))
+                keys.append((thr, c))
+        n_runs = sum(len(w[0]) for w in work)
+        if n_runs > 200000:   # large batches: NumPy releases the GIL, the (threshold, channel) groups run on host threads
+            if not hasattr(self, "_pool"):
+                from concurrent.futures import ThreadPoolExecutor
+                import os
+                self._pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
+            results = list(self._pool.map(one, work))
+        else:
+            results = [one(w) for w in work]
+        # insertion order of the reference: thresholds-major, min_lengths-minor (laugh_segmenter.py:87)
+        for (thr, c), res in zip(keys, results):
+            for ml, arr in zip(min_lengths, res):
+                out[c][(thr, ml)] = arr
         return out
 
     def __call__(self, pcm_host, chan_len, durations_s=None):
