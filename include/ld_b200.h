@@ -162,6 +162,13 @@ LD_API int64_t ld_train_debug_read(ld_ctx* ctx, int32_t kind, int32_t index, flo
  * of bytes required (including the terminating NUL); writes at most cap bytes. */
 LD_API int64_t ld_plan_json(const ld_config* cfg, char* buf, int64_t cap);
 
+/* Introspection (no GPU needed): JSON description of the tensor-core tap program of every conv launch of the plan --
+ * jobs (chains of output planes), their load groups (plane id, first pixel shift) and encoded MMA taps
+ * (ld_types.h: x = A offset | flags, y = B offset | LBO << 16, z = accumulator column, w = N/8 << 17) -- with plane ids in place of
+ * device addresses.  tests/ expand it back into (output, input, shift, weight tap) products and compare with ld_plan_json.
+ * Same return convention as ld_plan_json. */
+LD_API int64_t ld_gemm_program_json(const ld_config* cfg, char* buf, int64_t cap);
+
 /* Debug: copy one activation plane of the last processed chunk to the host as fp32 [rows][wp][C]. */
 LD_API int ld_debug_read_plane(ld_ctx* ctx, int32_t plane_id, int64_t rows, float* out_host);
 /* Executed multiply-accumulates per sequence row of the streaming plan, and kernel launches so far. */

@@ -57,6 +57,7 @@ SIGNATURES = {
     "ld_butter2_lowpass": (None, [c_double, POINTER(c_double), POINTER(c_double)]),
     "ld_infer_pcm_host": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_void_p, c_void_p]),
     "ld_plan_json": (c_int64, [POINTER(LdConfig), c_char_p, c_int64]),
+    "ld_gemm_program_json": (c_int64, [POINTER(LdConfig), c_char_p, c_int64]),
     "ld_debug_read_plane": (c_int, [c_void_p, c_int32, c_int64, c_void_p]),
     "ld_plan_macs_per_row": (c_double, [c_void_p]),
     "ld_plan_gemm_macs_per_row": (c_double, [c_void_p]),
@@ -123,6 +124,18 @@ def plan_json(cfg=None):
         raise LdError(lib.ld_last_error().decode())
     buf = ctypes.create_string_buffer(need)
     lib.ld_plan_json(ctypes.byref(cfg), buf, need)
+    return json.loads(buf.value.decode())
+
+
+def gemm_program_json(cfg=None):
+    """The tensor-core tap programs of the plan's conv launches as a dict (host builder only; runs without a GPU)."""
+    lib = load_library()
+    cfg = cfg if cfg is not None else default_config()
+    need = lib.ld_gemm_program_json(ctypes.byref(cfg), None, 0)
+    if need < 0:
+        raise LdError(lib.ld_last_error().decode())
+    buf = ctypes.create_string_buffer(need)
+    lib.ld_gemm_program_json(ctypes.byref(cfg), buf, need)
     return json.loads(buf.value.decode())
 
 

@@ -50,7 +50,7 @@ struct ConvWeights {
 };
 
 struct ConvLaunchDev {
-    ld::GemmLaunch h;   // passed to the kernel by value (__grid_constant__)
+    ld::GemmLaunch h;   // parameters (passed to the kernel by value, __grid_constant__) + the job table
     int wp = 0;
 };
 
@@ -81,7 +81,6 @@ struct ld_ctx {
     int rows_alloc = 0;   // rows per plane (chunk_rows + H)
     uint8_t* workspace = nullptr;
     size_t workspace_bytes = 0;
-    CUtensorMap* tmaps = nullptr;  // device array, one TMA descriptor per plane
     ld::TrainNet* train = nullptr;   // training network (ld_train_create)
     unsigned long long* gemm_prof = nullptr;  // LD_GEMM_PROF=1: 8 cycle counters per conv launch
     std::vector<PlaneDev> planes;
@@ -234,6 +233,78 @@ int64_t ld_plan_json(const ld_config* cfg, char* buf, int64_t cap) {
     }
 }
 
+// The MMA tap programs of every conv launch, built with plane ids in place of addresses (plane i "lives" at (i + 1) << 32).
+int64_t ld_gemm_program_json(const ld_config* cfg, char* buf, int64_t cap) {
+    try {
+        ld_config c;
+        if (cfg) c = *cfg; else ld_default_config(&c);
+        if (validate_config(c)) return -1;
+        ld::NetConfig net;
+        config_to_net(c, net);
+        const ld::Plan plan = ld::build_stream_plan(net);
+        const ld::GemmTuning tune = ld::gemm_tuning_from_env();
+        auto fake = [](int plane) { return reinterpret_cast<void*>(static_cast<uintptr_t>(plane + 1) << 32); };
+        auto plane_of = [](const void* p) { return static_cast<int>(reinterpret_cast<uintptr_t>(p) >> 32) - 1; };
+        std::string s = "{\"convs\":[";
+        std::vector<ld::GemmLaunch> launches(1);
+        for (size_t li = 0; li < plan.convs.size(); ++li) {
+            const auto& cs = plan.convs[li];
+            ld::GemmLaunch& L = launches[0];
+            std::memset(&L, 0, sizeof(L));
+            bool has_res = false;
+            for (const auto& other : plan.convs)
+                if (other.conv == cs.conv)
+                    for (const auto& js : other.jobs) has_res = has_res || js.res_plane >= 0;
+            L.cin = cs.cin; L.cout = cs.cout; L.n_wtaps = cs.ksize * cs.ksize + (has_res ? 1 : 0);
+            L.relu = cs.relu; L.wp = cs.wp; L.out_mode = cs.out_mode; L.wp2 = cs.wp2; L.hp = cs.hp;
+            L.w_stack = cs.ksize == 3 ? 1 : 0;
+            std::vector<ld::HostJob> jobs(cs.jobs.size());
+            for (size_t j = 0; j < cs.jobs.size(); ++j) {
+                const auto& js = cs.jobs[j];
+                for (const auto& t : js.taps) jobs[j].taps.push_back({fake(t.plane), 0, t.shift, t.wtap});
+                if (js.res_plane >= 0) jobs[j].taps.push_back({fake(js.res_plane), 0, js.res_shift, cs.ksize * cs.ksize});
+                jobs[j].out0 = fake(js.out0);
+                jobs[j].out1 = js.out1 >= 0 ? fake(js.out1) : nullptr;
+            }
+            std::string err;
+            if (!ld::gemm_build_launch(L, jobs, tune, err)) { fail(LD_ERR_INVALID, "conv " + cs.conv + ": " + err); return -1; }
+            if (li) s += ",";
+            s += "{\"conv\":\"" + cs.conv + "\",\"cin\":" + std::to_string(L.cin) + ",\"cout\":" + std::to_string(L.cout) +
+                 ",\"w_stack\":" + std::to_string(L.w_stack) + ",\"ext_alloc\":" + std::to_string(L.ext_alloc) +
+                 ",\"groups_per_stage\":" + std::to_string(L.groups_per_stage) + ",\"n_stages\":" + std::to_string(L.n_stages) +
+                 ",\"n_rings\":" + std::to_string(L.n_rings) + ",\"n_issuers\":" + std::to_string(L.n_issuers) + ",\"jobs\":[";
+            for (int j = 0; j < L.n_jobs; ++j) {
+                const ld::GemmJob& job = L.jobs[j];
+                if (j) s += ",";
+                s += "{\"n_stages\":" + std::to_string(job.n_stages) + ",\"outs\":[";
+                for (int o = 0; o < job.n_outs; ++o)
+                    s += (o ? ",[" : "[") + std::to_string(plane_of(job.outs[o].out0)) + "," +
+                         std::to_string(job.outs[o].out1 ? plane_of(job.outs[o].out1) : -1) + "]";
+                s += "],\"groups\":[";
+                for (int g = 0; g < job.n_groups; ++g)
+                    s += (g ? ",[" : "[") + std::to_string(plane_of(job.groups[g].src)) + "," + std::to_string(job.groups[g].shift) + "]";
+                s += "],\"taps\":[";
+                for (int t = 0; t < job.n_taps; ++t)
+                    s += (t ? ",[" : "[") + std::to_string(job.tapw[t].x) + "," + std::to_string(job.tapw[t].y) + "," +
+                         std::to_string(job.tapw[t].z) + "," + std::to_string(job.tapw[t].w) + "]";
+                s += "]}";
+            }
+            s += "]}";
+        }
+        s += "]}";
+        const int64_t need = static_cast<int64_t>(s.size()) + 1;
+        if (buf && cap > 0) {
+            const int64_t n = std::min<int64_t>(need, cap);
+            std::memcpy(buf, s.c_str(), static_cast<size_t>(n - 1));
+            buf[n - 1] = 0;
+        }
+        return need;
+    } catch (const std::exception& e) {
+        fail(LD_ERR_INVALID, e.what());
+        return -1;
+    }
+}
+
 int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
     if (!out) return fail(LD_ERR_INVALID, "out is null");
     *out = nullptr;
@@ -295,34 +366,6 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         ctx->planes[i].base = reinterpret_cast<__half*>(ctx->workspace + offs[i]) + guard * 8;
     }
 
-    // ---- one TMA descriptor per plane: (8 halfs, pixels incl. guards, C/8 chunks), box (8, kBoxPixels, C/8) --------
-    {
-        typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                          CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        LD_CUDA_C(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (fn == nullptr || qres != cudaDriverEntryPointSuccess)
-            return cleanup_fail(fail(LD_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver"));
-        std::vector<CUtensorMap> maps(plan.planes.size());
-        for (size_t i = 0; i < plan.planes.size(); ++i) {
-            const PlaneDev& pd = ctx->planes[i];
-            const cuuint64_t dims[3] = {8, static_cast<cuuint64_t>(pd.pixels_alloc), static_cast<cuuint64_t>(pd.C / 8)};
-            const cuuint64_t strides[2] = {16, static_cast<cuuint64_t>(pd.pixels_alloc) * 16};
-            const cuuint32_t box[3] = {8, static_cast<cuuint32_t>(ld::kBoxPixels), static_cast<cuuint32_t>(pd.C / 8)};
-            const cuuint32_t estr[3] = {1, 1, 1};
-            const CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(
-                &maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ctx->workspace + offs[i], dims, strides, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS)
-                return cleanup_fail(fail(LD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r))));
-        }
-        LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->tmaps), maps.size() * sizeof(CUtensorMap)));
-        LD_CUDA_C(cudaMemcpy(ctx->tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-    }
-
     // ---- weights (allocated now so that launch tables can point at them; filled by load_weights) -----
     for (const auto& cs : plan.convs) {
         if (ctx->weights.count(cs.conv)) continue;
@@ -360,6 +403,7 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         L.cin = cs.cin; L.cout = cs.cout; L.n_wtaps = cs.ksize * cs.ksize + (w.has_res ? 1 : 0);
         L.relu = cs.relu; L.wp = cs.wp; L.out_mode = cs.out_mode; L.wp2 = cs.wp2; L.hp = cs.hp;
         L.mode = 0;
+        L.w_stack = cs.ksize == 3 ? 1 : 0;
         L.prof = ctx->gemm_prof ? ctx->gemm_prof + 8 * li : nullptr;
         cd.wp = cs.wp;
         std::vector<ld::HostJob> jobs(cs.jobs.size());
@@ -371,7 +415,7 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
             for (const auto& t : taps) {
                 const PlaneDev& pd = ctx->planes[t.plane];
                 if (pd.C != cs.cin || pd.wp != cs.wp) return cleanup_fail(fail(LD_ERR_INVALID, "plan/plane mismatch in " + cs.conv));
-                jobs[j].taps.push_back({pd.base, pd.kc_stride, ctx->tmaps + t.plane, ld::kGuardRows * pd.wp + 256, t.shift, t.wtap});
+                jobs[j].taps.push_back({pd.base, pd.kc_stride, t.shift, t.wtap});
             }
             jobs[j].out0 = ctx->planes[js.out0].base;
             jobs[j].out1 = js.out1 >= 0 ? ctx->planes[js.out1].base : nullptr;
@@ -422,8 +466,8 @@ void ld_destroy(ld_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->workspace) cudaFree(ctx->workspace);
     if (ctx->train) ld::train_destroy(ctx->train);
-    if (ctx->tmaps) cudaFree(ctx->tmaps);
     if (ctx->gemm_prof) cudaFree(ctx->gemm_prof);
+    for (auto& cd : ctx->convs) ld::gemm_release(cd.h);
     for (auto& kv : ctx->weights) {
         if (kv.second.w) cudaFree(kv.second.w);
         if (kv.second.shift) cudaFree(kv.second.shift);

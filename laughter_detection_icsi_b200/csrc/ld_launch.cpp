@@ -1,9 +1,11 @@
-// Host-side construction of a GemmLaunch (ld_types.h) from per-job tap lists: sorts the taps, merges taps that can share
-// one smem load into groups, sizes the smem ring, chooses the pipeline shape and encodes the tap program the MMA warps
-// execute.  Shared by the inference context (ld_api.cu) and the training network (ld_train.cu).
+// Host-side construction of a GemmLaunch (ld_types.h) from per-output tap lists: finds the chains of output planes that
+// share input planes, packs them into jobs, merges the taps of one input operand that feed adjacent outputs into single
+// wide-N MMAs, assigns the loads to smem stages, sizes the ring and encodes the tap program the MMA warps execute.
+// Shared by the inference context (ld_api.cu) and the training network (ld_train.cu).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <tuple>
 
 #include "ld_net.h"
 #include "ld_types.h"
@@ -13,97 +15,178 @@ namespace ld {
 GemmTuning gemm_tuning_from_env() {
     auto env_int = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
     GemmTuning t;
-    t.loader = env_int("LD_GEMM_LOADER", 0);
     t.group_span = env_int("LD_GEMM_SPAN", 2);
-    if (t.loader == 1) t.group_span = std::min(t.group_span, kBoxPixels - kTileM);
     t.max_stages = env_int("LD_GEMM_STAGES", 16);
-    t.tile_stage_cin = env_int("LD_GEMM_TILE_STAGE_CIN", 32);
-    t.align_loads = env_int("LD_GEMM_ALIGN", 0);
+    t.stage_bytes = env_int("LD_GEMM_STAGE_BYTES", 18 * 1024);
+    t.max_outs = env_int("LD_GEMM_MAX_OUTS", kMaxOuts);
+    t.issuers_wide = env_int("LD_GEMM_ISSUERS_WIDE", 2);
+    t.issuers_narrow = env_int("LD_GEMM_ISSUERS_NARROW", 4);
     t.n_rings_max = env_int("LD_GEMM_RINGS", 2);
     return t;
 }
 
-// The caller presets L's header (weights, shift, cin, cout, n_wtaps, relu, wp, out_mode, wp2, hp, mode, stats, prof).
-bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& jobs, const GemmTuning& tune, std::string& err) {
-    if (jobs.empty() || jobs.size() > static_cast<size_t>(kMaxJobs)) { err = "bad job count"; return false; }
-    L.n_jobs = static_cast<int>(jobs.size());
-    L.loader = tune.loader;
-    struct TapInfo { int group[kMaxTaps], off[kMaxTaps], wslab[kMaxTaps]; };
-    std::vector<TapInfo> info(jobs.size());
-    int ext_max = 0;
-    for (size_t j = 0; j < jobs.size(); ++j) {
+namespace {
+
+struct Tap {          // one (input operand, weight slab) product feeding output `out` of a job
+    const void* src;
+    long long kc_stride;
+    int shift, wslab, out;
+    int group, off;   // load group inside the job, pixel offset inside the group
+};
+
+bool shares_input(const HostJob& a, const HostJob& b) {
+    for (const auto& x : a.taps)
+        for (const auto& y : b.taps)
+            if (x.src == y.src && x.shift == y.shift) return true;
+    return false;
+}
+
+}  // namespace
+
+static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, int max_outs, std::string& err);
+
+// The caller presets L's header (weights, shift, cin, cout, n_wtaps, w_stack, relu, wp, out_mode, wp2, hp, mode, stats, prof).
+bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, std::string& err) {
+    if (outs.empty()) { err = "no outputs"; return false; }
+    { const char* v = std::getenv("LD_GEMM_DBG"); L.dbg = v ? std::atoi(v) : 0; }
+    if (L.w_stack && L.n_wtaps < 9) { err = "stacked weights need a 3x3 kernel"; return false; }
+    // cout >= 48: two issuers with 256 accumulator columns each (chains of up to 4 outputs); narrower layers are bound by
+    // the issue latency of their small MMAs: four issuers with 128 columns each
+    L.n_issuers = L.cout >= 48 ? tune.issuers_wide : tune.issuers_narrow;
+    if (L.n_issuers != 2 && L.n_issuers != 4) { err = "2 or 4 MMA issuers"; return false; }
+    // the longest chains whose loads and taps fit a job (stride-2 layers merge nothing: their chains stay short)
+    const int max_outs = L.w_stack ? std::max(1, std::min({tune.max_outs, kMaxOuts, kTmemCols / L.n_issuers / L.cout})) : 1;
+    for (int mo = max_outs; mo >= 1; --mo)
+        if (build_with(L, outs, tune, mo, err)) return true;
+    return false;
+}
+
+static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, const int max_outs, std::string& err) {
+    const int kchunks = L.cin / 8;
+    const bool stack = L.w_stack != 0;
+
+    // ---- 1. jobs: maximal runs of consecutive outputs that share an input operand, cut into near-equal parts that fit TMEM
+    std::vector<std::pair<int, int>> parts;  // [first, last) output indices
+    for (size_t a = 0; a < outs.size();) {
+        size_t b = a + 1;
+        while (max_outs > 1 && b < outs.size() && shares_input(outs[b - 1], outs[b])) ++b;
+        const int n = static_cast<int>(b - a), n_parts = (n + max_outs - 1) / max_outs;
+        for (int i = 0; i < n_parts; ++i)
+            parts.push_back({static_cast<int>(a) + i * n / n_parts, static_cast<int>(a) + (i + 1) * n / n_parts});
+        a = b;
+    }
+    if (parts.size() > static_cast<size_t>(kMaxJobs)) { err = "too many jobs"; return false; }
+    L.n_jobs = static_cast<int>(parts.size());
+
+    // ---- 2. per job: load groups (taps of one plane within group_span pixels share a load), in chain order
+    std::vector<std::vector<Tap>> job_taps(parts.size());
+    int ext_max = 0, max_groups = 1;
+    for (size_t j = 0; j < parts.size(); ++j) {
         GemmJob& job = L.jobs[j];
         std::memset(&job, 0, sizeof(job));
-        std::vector<HostTap> taps = jobs[j].taps;
-        std::sort(taps.begin(), taps.end(), [](const HostTap& a, const HostTap& b) {
-            return a.src != b.src ? a.src < b.src : a.shift < b.shift;
+        std::vector<Tap>& taps = job_taps[j];
+        for (int o = parts[j].first; o < parts[j].second; ++o) {
+            if (outs[o].taps.empty()) { err = "output without taps"; return false; }
+            for (const auto& t : outs[o].taps) taps.push_back({t.src, t.kc_stride, t.shift, t.wslab, o - parts[j].first, -1, 0});
+            job.outs[o - parts[j].first] = {static_cast<__half*>(outs[o].out0), static_cast<__half*>(outs[o].out1)};
+            if (outs[o].out_kc_stride != outs[parts[j].first].out_kc_stride) { err = "outputs of a job differ in layout"; return false; }
+        }
+        job.n_outs = parts[j].second - parts[j].first;
+        job.out_kc_stride = outs[parts[j].first].out_kc_stride;
+        std::sort(taps.begin(), taps.end(), [](const Tap& a, const Tap& b) {
+            return std::tie(a.src, a.shift, a.out) < std::tie(b.src, b.shift, b.out);
         });
-        if (taps.empty() || taps.size() > static_cast<size_t>(kMaxTaps)) { err = "bad tap count"; return false; }
-        int g = -1, g_min = 0;
-        const void* g_src = nullptr;
-        int group_ext[kMaxGroups] = {0};
-        for (size_t t = 0; t < taps.size(); ++t) {
-            if (g < 0 || taps[t].src != g_src || taps[t].shift - g_min > tune.group_span + (tune.align_loads ? 7 : 0)) {
-                if (++g >= kMaxGroups) { err = "too many load groups"; return false; }
-                g_src = taps[t].src; g_min = taps[t].shift;
-                // optionally start every copy on a 128-byte boundary of the plane (8 pixels)
-                if (tune.align_loads) g_min -= ((g_min % 8) + 8) % 8;
-                job.groups[g].src = static_cast<const __half*>(taps[t].src);
-                job.groups[g].kc_stride = taps[t].kc_stride;
-                job.groups[g].tmap = taps[t].tmap;
-                job.groups[g].pixel0 = taps[t].pixel0;
-                job.groups[g].shift = g_min;
-                group_ext[g] = kTileM;
-            }
-            group_ext[g] = std::max(group_ext[g], kTileM + taps[t].shift - g_min);
-            info[j].group[t] = g;
-            info[j].off[t] = taps[t].shift - g_min;
-            info[j].wslab[t] = taps[t].wslab;
+        struct Group { const void* src; long long kc_stride; int g_min, ext, order; };
+        std::vector<Group> groups;
+        for (auto& t : taps) {
+            if (groups.empty() || groups.back().src != t.src || t.shift - groups.back().g_min > tune.group_span)
+                groups.push_back({t.src, t.kc_stride, t.shift, kTileM, 1 << 30});
+            Group& g = groups.back();
+            g.ext = std::max(g.ext, kTileM + t.shift - g.g_min);
+            // chain position of the operand: input row = output row + ky - 1 (identity / 1x1 taps sit at their output)
+            const int ky = (stack && t.wslab < 9) ? t.wslab / 3 : 1;
+            g.order = std::min(g.order, 4 * (t.out + ky - 1) + ((stack && t.wslab >= 9) ? 1 : 0));
+            t.group = static_cast<int>(groups.size()) - 1;
+            t.off = t.shift - g.g_min;
         }
-        job.n_groups = g + 1;
-        job.n_taps = static_cast<int>(taps.size());
-        for (int q = 0; q < job.n_groups; ++q) ext_max = std::max(ext_max, group_ext[q]);
-        job.out0 = static_cast<__half*>(jobs[j].out0);
-        job.out1 = static_cast<__half*>(jobs[j].out1);
-        job.out_kc_stride = jobs[j].out_kc_stride;
+        if (groups.size() > static_cast<size_t>(kMaxGroups)) { err = "too many load groups"; return false; }
+        std::vector<int> perm(groups.size()), rank(groups.size());
+        for (size_t i = 0; i < perm.size(); ++i) perm[i] = static_cast<int>(i);
+        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return groups[a].order < groups[b].order; });
+        for (size_t i = 0; i < perm.size(); ++i) {
+            rank[perm[i]] = static_cast<int>(i);
+            const Group& g = groups[perm[i]];
+            job.groups[i] = {static_cast<const __half*>(g.src), g.kc_stride, g.g_min, 0};
+            ext_max = std::max(ext_max, g.ext);
+        }
+        for (auto& t : taps) t.group = rank[t.group];
+        job.n_groups = static_cast<int>(groups.size());
+        max_groups = std::max(max_groups, job.n_groups);
     }
-    if (tune.loader == 1) {
-        if (ext_max > kBoxPixels) { err = "tap span exceeds the TMA box"; return false; }
-        L.ext_alloc = kBoxPixels;
-    } else {
-        L.ext_alloc = (ext_max + 7) & ~7;
-    }
-    // small-K layers: one smem stage (one barrier round trip) per TILE instead of per group
-    int max_groups = 1;
-    for (int j = 0; j < L.n_jobs; ++j) max_groups = std::max(max_groups, L.jobs[j].n_groups);
-    L.groups_per_stage = (tune.tile_stage_cin > 0 && L.cin <= tune.tile_stage_cin) ? max_groups : 1;
+    L.ext_alloc = (ext_max + 7) & ~7;
     L.wp_magic = static_cast<uint32_t>((1ull << 32) / static_cast<unsigned>(L.wp)) + 1u;
-    L.n_stages = gemm_pick_stages(L.cin, L.cout, L.n_wtaps, L.ext_alloc, L.groups_per_stage, tune.max_stages);
-    {   // two rings when half of the stages still hold two whole tiles (tile-stage: one stage each; per-group: max_groups);
-        // per-group launches whose half ring would hold less measured slower with two rings
-        const int need = L.groups_per_stage > 1 ? 1 : max_groups;
-        if (L.n_stages < need || L.n_stages < 2) { err = "smem ring shorter than one tile"; return false; }
-        L.n_rings = (tune.n_rings_max >= 2 && L.n_stages / 2 >= 2 * need) ? 2 : 1;
-        if (L.n_rings == 2) L.n_stages &= ~1;
+
+    // ---- 3. smem ring: a stage holds consecutive groups of a job up to ~stage_bytes (small-K layers: fewer barrier trips)
+    const int box_bytes = L.ext_alloc * 16 * kchunks;
+    L.groups_per_stage = std::max(1, std::min(max_groups, tune.stage_bytes / box_bytes));
+    L.n_stages = gemm_pick_stages(L.cin, L.cout, L.n_wtaps, L.n_jobs, L.ext_alloc, L.groups_per_stage, tune.max_stages);
+    while (L.n_stages < 4 && L.groups_per_stage > 1) {
+        --L.groups_per_stage;
+        L.n_stages = gemm_pick_stages(L.cin, L.cout, L.n_wtaps, L.n_jobs, L.ext_alloc, L.groups_per_stage, tune.max_stages);
     }
-    // the tap program the MMA warp executes (ld_types.h: kTapFirst / kTapLast / kTapPass)
-    const uint32_t kchunks = static_cast<uint32_t>(L.cin / 8);
-    for (int j = 0; j < L.n_jobs; ++j) {
+    if (L.n_stages < 2) { err = "smem ring shorter than two stages"; return false; }
+    L.n_rings = (tune.n_rings_max >= 2 && L.n_stages >= 6) ? 2 : 1;
+    if (L.n_rings == 2) L.n_stages &= ~1;
+
+    // ---- 4. the tap program: per group, per pixel offset, runs of adjacent outputs with adjacent weight rows -> one MMA
+    const int gps = L.groups_per_stage;
+    const uint32_t box16 = static_cast<uint32_t>(L.ext_alloc) * kchunks;
+    for (size_t j = 0; j < parts.size(); ++j) {
         GemmJob& job = L.jobs[j];
-        const TapInfo& ti = info[j];
-        const uint32_t box16 = static_cast<uint32_t>(L.ext_alloc) * kchunks;
-        const bool tile_stage = L.groups_per_stage > 1;
-        int last_first = 0;
-        for (int t = 0; t < job.n_taps; ++t) {
-            const uint32_t a16 = (tile_stage ? ti.group[t] * box16 : 0u) + static_cast<uint32_t>(ti.off[t]);
-            const uint32_t b16 = static_cast<uint32_t>(ti.wslab[t]) * kchunks * L.cout;
-            const bool first = tile_stage ? t == 0 : (t == 0 || ti.group[t] != ti.group[t - 1]);
-            const bool last = tile_stage ? t == job.n_taps - 1 : (t == job.n_taps - 1 || ti.group[t] != ti.group[t + 1]);
-            if (a16 >= (1u << 14) || b16 >= (1u << 14)) { err = "tap offset overflow"; return false; }
-            job.tapw[t] = a16 | (b16 << 14) | (first ? kTapFirst : 0u) | (last ? kTapLast : 0u);
-            if (first) last_first = t;
+        std::vector<Tap>& taps = job_taps[j];
+        // weight row block of a tap inside its stacked block (ky = 2, 1, 0), or -1 for a stand-alone slab
+        auto wrow = [&](const Tap& t) { return (stack && t.wslab < 9) ? 2 - t.wslab / 3 : -1; };
+        auto kx_of = [&](const Tap& t) { return (stack && t.wslab < 9) ? t.wslab % 3 : t.wslab; };
+        std::sort(taps.begin(), taps.end(), [&](const Tap& a, const Tap& b) {
+            return std::make_tuple(a.group, a.off, kx_of(a), a.out) < std::make_tuple(b.group, b.off, kx_of(b), b.out);
+        });
+        job.n_stages = (job.n_groups + gps - 1) / gps;
+        int n = 0, last_first = -1;
+        for (size_t i = 0; i < taps.size();) {
+            size_t e = i + 1;
+            if (wrow(taps[i]) >= 0)
+                while (e < taps.size() && taps[e].group == taps[i].group && taps[e].off == taps[i].off &&
+                       kx_of(taps[e]) == kx_of(taps[i]) && wrow(taps[e]) >= 0 && taps[e].out == taps[e - 1].out + 1 &&
+                       wrow(taps[e]) == wrow(taps[e - 1]) + 1)
+                    ++e;
+            if (n >= kMaxTaps) { err = "too many MMA taps in a job"; return false; }
+            const Tap& t = taps[i];
+            const int n_merged = static_cast<int>(e - i);
+            const uint32_t a16 = static_cast<uint32_t>(t.group % gps) * box16 + static_cast<uint32_t>(t.off);
+            uint32_t b16, lbo16;
+            if (wrow(t) >= 0) {
+                b16 = static_cast<uint32_t>(kx_of(t)) * kchunks * 3u * L.cout + static_cast<uint32_t>(wrow(t)) * L.cout;
+                lbo16 = 3u * L.cout;
+            } else {
+                b16 = static_cast<uint32_t>(t.wslab) * kchunks * L.cout;
+                lbo16 = static_cast<uint32_t>(L.cout);
+            }
+            if (a16 >= (1u << 14) || b16 >= (1u << 13)) { err = "tap offset overflow"; return false; }
+            const int stage_of = t.group / gps;
+            const bool first = i == 0 || taps[i - 1].group / gps != stage_of;
+            const bool last = e == taps.size() || taps[e].group / gps != stage_of;
+            const uint32_t col = static_cast<uint32_t>(t.out) * L.cout, ncols = static_cast<uint32_t>(n_merged) * L.cout;
+            if (col + ncols > static_cast<uint32_t>(kTmemCols / L.n_issuers)) { err = "accumulator overflow"; return false; }
+            job.tapw[n].x = a16 | (first ? kTapFirst : 0u) | (last ? kTapLast : 0u);
+            job.tapw[n].y = b16 | (lbo16 << 16);
+            job.tapw[n].z = col;
+            job.tapw[n].w = (ncols >> 3) << 17;
+            if (first) last_first = n;
+            ++n;
+            i = e;
         }
-        job.tapw[last_first] |= kTapPass;
+        job.tapw[last_first].x |= kTapPass;
+        job.n_taps = n;
     }
     return true;
 }

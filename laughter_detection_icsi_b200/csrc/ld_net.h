@@ -55,26 +55,25 @@ cudaError_t launch_head(const HeadLaunch& L, const ChannelTable& ct, float* prob
                         cudaStream_t stream);
 
 // ld_gemm.cu
-cudaError_t launch_gemm_taps(const GemmLaunch& h, int m_tiles, int M, int num_sms, cudaStream_t stream);
-int gemm_pick_stages(int cin, int cout, int n_wtaps, int ext_alloc, int groups_per_stage, int max_stages);
+cudaError_t launch_gemm_taps(GemmLaunch& h, int m_tiles, int M, int num_sms, cudaStream_t stream);
+void gemm_release(GemmLaunch& h);   // frees the device copy of the job table
+int gemm_pick_stages(int cin, int cout, int n_wtaps, int n_jobs, int ext_alloc, int groups_per_stage, int max_stages);
 
 // ld_launch.cpp
 struct HostTap {
     const void* src;      // pixel 0, chunk 0 of the source plane
     long long kc_stride;  // elements between its channel chunks
-    const void* tmap;     // optional CUtensorMap (loader 1)
-    int pixel0;           // tensor coordinate of pixel 0 (loader 1)
     int shift;            // pixel shift of the tap
-    int wslab;            // weight slab index
+    int wslab;            // weight slab index (3x3: ky * 3 + kx; 9: the identity / shortcut slab)
 };
-struct HostJob {
+struct HostJob {   // one OUTPUT plane; gemm_build_launch packs chains of them into GemmJobs
     std::vector<HostTap> taps;
     void* out0 = nullptr;
     void* out1 = nullptr;
     long long out_kc_stride = 0;
 };
 struct GemmTuning {
-    int loader, group_span, max_stages, tile_stage_cin, align_loads, n_rings_max;
+    int group_span, max_stages, stage_bytes, max_outs, n_rings_max, issuers_wide, issuers_narrow;
 };
 GemmTuning gemm_tuning_from_env();
 bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& jobs, const GemmTuning& tune, std::string& err);

@@ -151,6 +151,19 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                  : "memory");
 }
 
+// TMEM -> registers: 32 lanes x 32-bit, 8 consecutive columns per thread.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
+}
+
 // TMEM -> registers: 32 lanes x 32-bit, 16 consecutive columns per thread.
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -177,16 +190,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         : "r"(taddr)
         : "memory");
 }
+// registers -> TMEM: zero 16 consecutive columns of this warp's 32 lanes (accumulators are cleared by the epilogue so
+// that every MMA of a tile can accumulate, whichever output columns it covers).
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(z)
+        : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_zero_cols(uint32_t taddr) {
+    static_assert(N % 8 == 0, "accumulator width");
+#pragma unroll
+    for (int c = 0; c + 16 <= N; c += 16) tmem_st16_zero(taddr + c);
+    if (N % 16) tmem_st8_zero(taddr + N / 16 * 16);
+}
+__device__ __forceinline__ void tmem_wait_st() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // N consecutive accumulator columns (N a multiple of 16); the caller issues tmem_wait_ld() once afterwards.
 template <int N>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[N]) {
-    static_assert(N % 16 == 0 && N >= 16 && N <= 128, "accumulator width");
+    static_assert(N % 8 == 0 && N >= 8 && N <= 128, "accumulator width");
+    constexpr int n32 = N / 32 * 32, n16 = (N - n32) / 16 * 16;
 #pragma unroll
-    for (int c = 0; c + 32 <= N; c += 32) tmem_ld32(taddr + c, v + c);
-    if (N % 32 != 0) {
-        uint32_t(&t)[16] = *reinterpret_cast<uint32_t(*)[16]>(v + (N - 16));
-        tmem_ld16(taddr + (N - 16), t);
+    for (int c = 0; c < n32; c += 32) tmem_ld32(taddr + c, v + c);
+    if (n16) {
+        uint32_t(&t)[16] = *reinterpret_cast<uint32_t(*)[16]>(v + n32);
+        tmem_ld16(taddr + n32, t);
     }
+    if (N - n32 - n16) tmem_ld8(taddr + n32 + n16, v + n32 + n16);
 }
 
 // 16-byte read-only global load that does not allocate in L1 (streamed once per tile).

@@ -647,6 +647,7 @@ public:
         if (head_scratch) cudaFree(head_scratch);
         if (x_keep) cudaFree(x_keep);
         if (bn_items) cudaFree(bn_items);
+        for (auto& c : convs) { gemm_release(c.fwd); gemm_release(c.bwd); }
     }
 
     // ---- allocation: bf16 chunk-planar planes with zero guards, carved from one zero-initialised workspace
@@ -732,7 +733,6 @@ TrainNet* train_create(int max_batch, int num_sms, const NetConfig& cfg, std::st
     TrainNet* n = new TrainNet();
     n->max_batch = max_batch; n->num_sms = num_sms; n->cfg = cfg;
     n->tune = gemm_tuning_from_env();
-    n->tune.loader = 0;
     if (const char* v = std::getenv("LD_WGRAD")) n->wgrad_mma = std::string(v) != "cuda";
 
     // ---- topology, parameter table (module registration order of the reference's ResNetBigger) and sizes
@@ -1028,7 +1028,7 @@ inline unsigned ew_grid(const TrainNet* n, long long items) {
     return static_cast<unsigned>(std::max<long long>(1, std::min<long long>((items + 255) / 256, static_cast<long long>(n->num_sms) * 16)));
 }
 
-cudaError_t run_gemm(TrainNet* n, const GemmLaunch& L, const TPlane& geom, cudaStream_t stream, std::string& err) {
+cudaError_t run_gemm(TrainNet* n, GemmLaunch& L, const TPlane& geom, cudaStream_t stream, std::string& err) {
     const long long M = static_cast<long long>(n->B) * geom.hp * geom.wp;
     const int m_tiles = static_cast<int>((M + kTileM - 1) / kTileM);
     ++n->launches;

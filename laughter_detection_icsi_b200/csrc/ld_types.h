@@ -19,39 +19,54 @@
 namespace ld {
 
 constexpr int kTileM = 128;      // output pixels per MMA tile (UMMA M)
-constexpr int kBoxPixels = 136;  // pixels per TMA box: a tile plus the +-1 pixel halo of a 3-tap row, rounded to 8
-constexpr int kMaxGroups = 6;    // distinct smem loads per job
-constexpr int kMaxTaps = 10;     // MMA taps per job (3x3 = 9)
-constexpr int kMaxJobs = 16;     // jobs (output planes) per launch
+constexpr int kMaxGroups = 16;   // distinct smem loads per job
+constexpr int kMaxTaps = 32;     // MMA taps per job
+constexpr int kMaxOuts = 8;      // output planes per job (their accumulators sit side by side in TMEM)
+constexpr int kTmemCols = 512;   // accumulator columns per SM, split into n_issuers stages: n_outs * cout <= 512 / n_issuers
+constexpr int kMaxJobs = 16;     // jobs per launch (the planner also splits a layer into launches of at most this many output planes)
 constexpr int kGuardRows = 104;  // zero guard rows allocated before/after every plane
 
 enum OutMode : int32_t { OUT_PLAIN = 0, OUT_COLSPLIT = 1 };
 
 // ---- device-side launch description (passed to the kernel BY VALUE as a __grid_constant__ parameter: every field the
 // warp-specialised roles index is then read through the uniform constant path, no shared-memory staging) ----
+//
+// A JOB is a set of up to kMaxOuts output planes that are computed together for one tile of 128 pixels.  The output planes
+// of a ResNet conv layer come in chains (local rows j, j+1, ... of the window): input row i feeds output rows i-1, i, i+1
+// with the weight rows ky = 2, 1, 0.  The kernel therefore walks the INPUT planes of the chain: each is loaded into shared
+// memory once and multiplied by the weights of all the outputs it feeds in ONE MMA whose N spans their accumulators
+// (weights stacked [ky=2 | ky=1 | ky=0] along N in shared memory, accumulators side by side in TMEM in chain order).
+// An SS-mode MMA re-reads its 4 KB A operand whatever N is, so this divides the shared-memory operand traffic -- the
+// measured limiter of every layer of this net (cout <= 64) -- by up to three.
 struct GemmGroup {
     const __half* src;   // pixel 0, chunk 0 of the source plane
     int64_t kc_stride;   // elements between channel chunks of the source plane
-    const void* tmap;    // CUtensorMap of the source plane: (8 halfs, pixels incl. guards, C/8 chunks), box (8, kBoxPixels, C/8)
-    int32_t pixel0;      // tensor coordinate of the plane's pixel 0 (= guard pixels in front of it)
     int32_t shift;       // first pixel to load relative to the tile's first output pixel
+    int32_t pad_;
 };
-// One MMA tap as the issuing warp sees it (16-byte smem-descriptor units):
-//   bits 0..13  A offset inside the current smem stage (group slot + pixel shift)    bits 14..27  B offset of the weight slab
-//   bit 28      first tap of a stage: wait for its "full" barrier                   bit 29       last tap of a stage: commit "empty"
-constexpr uint32_t kTapFirst = 1u << 28, kTapLast = 1u << 29;
-constexpr uint32_t kTapPass = 1u << 30;  // this tap's wait is the tile's last one: the next issuer warp may start waiting
-constexpr int kTapWords = 12;  // kMaxTaps rounded up to whole 16-byte loads
-struct alignas(16) GemmJob {
-    uint32_t tapw[kTapWords];
-    GemmGroup groups[kMaxGroups];
-    int32_t n_groups, n_taps;
+// One MMA tap as the issuing warp sees it, pre-digested on the host (offsets in 16-byte smem-descriptor units):
+//   x: bits 0..13  A offset inside the current smem stage (group slot + pixel shift)
+//      bit 28 first tap of a stage: wait for its "full" barrier      bit 29 last tap of a stage: commit "empty"
+//      bit 30 this wait is the tile's last one: the ring's other issuer may start waiting
+//   y: low word of the B smem descriptor relative to the weights: bits 0..13 offset of the weight rows, bits 16..29 LBO
+//      (rows per channel chunk: 3 * cout inside a stacked block, cout for a stand-alone slab [cin/8][cout][8])
+//   z: first accumulator column                w: N / 8 << 17 (the N field of the instruction descriptor)
+constexpr uint32_t kTapFirst = 1u << 28, kTapLast = 1u << 29, kTapPass = 1u << 30;
+struct GemmOut {
     __half* out0;  // PLAIN: the plane; COLSPLIT: even-column plane
     __half* out1;  // COLSPLIT: odd-column plane
-    int64_t out_kc_stride;
 };
-struct GemmLaunch {
-    GemmJob jobs[kMaxJobs];
+struct alignas(16) GemmJob {
+    uint4 tapw[kMaxTaps];
+    GemmGroup groups[kMaxGroups];
+    GemmOut outs[kMaxOuts];
+    int32_t n_groups, n_taps, n_outs, n_stages;  // n_stages = ceil(n_groups / groups_per_stage)
+    int64_t out_kc_stride;
+    int64_t pad_;
+};
+struct GemmParams {         // the kernel's __grid_constant__ parameter
+    const GemmJob* jobs_dev;  // [n_jobs] in device memory; every CTA copies the table into shared memory (the roles index it
+                              // per tile and per tap: the constant path thrashes on a table of this size)
     const __half* weights;  // [n_wtaps][cin/8][cout][8] fp16, BatchNorm scale folded in
     const float* shift;     // [cout] folded BatchNorm shift (+ conv bias)
     int32_t n_jobs, cin, cout, n_wtaps;
@@ -59,13 +74,18 @@ struct GemmLaunch {
     int32_t ext_alloc;  // pixels per loaded group (>= every group's extent, multiple of 8)
     int32_t hp;         // >0: rows per image incl. 2 pad rows (dense layout), pad rows forced to zero
     int32_t n_stages;
-    int32_t loader;     // 0: one bulk copy per channel chunk; 1: one TMA tensor copy per group
-    int32_t groups_per_stage;  // 1: every group has its own smem stage/barrier; >1: a stage holds all groups of a tile
+    int32_t groups_per_stage;  // consecutive groups of a job that share one smem stage (one barrier round trip)
     uint32_t wp_magic;  // floor(2^32 / wp) + 1: row = umulhi(pixel, wp_magic)
+    int32_t w_stack;    // 1: 3x3 weights are re-stacked in smem as [kx][cin/8][ky = 2,1,0][cout][8] (slab 9, if any, stays a slab)
+    int32_t dbg;        // timing experiments only (LD_GEMM_DBG): 1 = producers copy one group per stage (results are garbage)
+    int32_t n_issuers;  // MMA-issuing warps = accumulator stages (2: 256 columns each, 4: 128 columns each)
     int32_t n_rings;    // 2: two producer/issuer pipelines over half the stages each; 1: a single ring
     int32_t mode;       // 0: inference (fp16, shift + ReLU epilogue); 1: training (bf16, raw output + channel statistics)
     float* stats;       // mode 1: [2 * cout] per-channel sum and sum of squares (atomically accumulated), or null
     unsigned long long* prof;  // optional: 8 cycle counters per launch (see ld_gemm.cu), null = off
+};
+struct GemmLaunch : GemmParams {   // host side: the parameters plus the job table gemm_build_launch fills;
+    GemmJob jobs[kMaxJobs];        // launch_gemm_taps uploads it on first use (jobs_dev), gemm_release frees it
 };
 
 // ---- host-side plan (plane ids instead of pointers) ----

@@ -57,3 +57,68 @@ def test_emulated_plan_fp16_error_budget():
     ref = resnet_oracle.window_probs(sd, feats)
     out = PlanEmulator(plan, sd, half=True).run(torch.from_numpy(feats), 40).numpy()
     assert np.abs(out - ref).max() < 1e-3
+
+
+def _expand_tap_program(conv):
+    """Decode the encoded MMA taps of one conv launch (ld_types.h) back into (out plane, src plane, shift, weight tap)
+    products, checking the stage bookkeeping flags on the way."""
+    cin, cout, gps = conv["cin"], conv["cout"], conv["groups_per_stage"]
+    kchunks, box16 = cin // 8, conv["ext_alloc"] * (cin // 8)
+    products = []
+    for job in conv["jobs"]:
+        stage, n_first, n_last, n_pass, open_stage = -1, 0, 0, 0, False
+        assert len(job["outs"]) * cout <= 512 // conv["n_issuers"]
+        for x, y, z, w in job["taps"]:
+            a16, b16, lbo16 = x & 0x3FFF, y & 0x3FFF, (y >> 16) & 0x3FFF
+            first, last, passing = bool(x & (1 << 28)), bool(x & (1 << 29)), bool(x & (1 << 30))
+            slab = lbo16 == cout
+            assert lbo16 in (cout, 3 * cout) and y >> 30 == 0
+            if first:
+                assert not open_stage
+                stage += 1; n_first += 1; open_stage = True
+            assert open_stage, "tap outside a stage"
+            if passing:
+                assert first
+                n_pass += 1
+            col, n = z, (w >> 17) * 8
+            assert w & ((1 << 17) - 1) == 0 and col + n <= 512 // conv["n_issuers"]
+            assert n % cout == 0 and col % cout == 0 and n % 16 == 0 and 16 <= n <= 256
+            g = stage * gps + a16 // box16
+            off = a16 % box16
+            assert g < len(job["groups"]) and off <= conv["ext_alloc"] - 128
+            src, gshift = job["groups"][g]
+            for i in range(n // cout):
+                if slab:
+                    assert n == cout and b16 % (kchunks * cout) == 0
+                    wtap = b16 // (kchunks * cout)
+                else:
+                    assert conv["w_stack"] == 1
+                    kx, rem = divmod(b16, kchunks * 3 * cout)
+                    assert rem % cout == 0 and rem // cout + n // cout <= 3
+                    wtap = (2 - (rem // cout + i)) * 3 + kx
+                products.append((job["outs"][col // cout + i][0], src, gshift + off, wtap))
+            if last:
+                n_last += 1; open_stage = False
+        assert not open_stage and n_first == n_last == job["n_stages"] == -(-len(job["groups"]) // gps) and n_pass == 1
+        assert stage == job["n_stages"] - 1
+    return products
+
+
+def test_tap_program_covers_the_plan():
+    """The N-stacked tap programs (chains of outputs, merged MMAs) multiply exactly the products the plan lists."""
+    plan = _native.plan_json()
+    prog = _native.gemm_program_json()
+    assert [c["conv"] for c in prog["convs"]] == [c["conv"] for c in plan["convs"]]
+    merged = 0
+    for pc, gc in zip(plan["convs"], prog["convs"]):
+        want = []
+        for job in pc["jobs"]:
+            want += [(job["out0"], p, s, t) for p, s, t in job["taps"]]
+            if job["res"] >= 0:
+                want.append((job["out0"], job["res"], job.get("res_shift", 0), pc["ksize"] ** 2))
+        got = _expand_tap_program(gc)
+        assert sorted(got) == sorted(want), gc["conv"]
+        assert [tuple(o) for j in gc["jobs"] for o in j["outs"]] == [(j["out0"], j["out1"]) for j in pc["jobs"]]
+        merged += len(want) - sum(len(j["taps"]) for j in gc["jobs"])
+        assert gc["n_stages"] >= 2 and gc["n_rings"] in (1, 2) and gc["n_issuers"] in (2, 4)
+    assert merged > 300, "chains of window-specific rows share their input loads and MMAs"

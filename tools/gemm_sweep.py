@@ -13,11 +13,11 @@ from laughter_detection_icsi_b200.engine import Engine  # noqa: E402
 NAMES = ["prod_wait", "mma_wait_full", "mma_wait_acc", "mma_issue", "epi_wait", "epi_work", "cta", "tiles"]
 
 
-def run(label, env, minutes, detail=False):
-    for k in ("LD_GEMM_LOADER", "LD_GEMM_SPAN", "LD_GEMM_STAGES", "LD_GEMM_PROF", "LD_GEMM_TILE_STAGE_CIN", "LD_GEMM_ALIGN", "LD_GEMM_RINGS"):
+def run(label, env, minutes, detail=False, chunk_rows=0):
+    for k in ("LD_GEMM_LOADER", "LD_GEMM_SPAN", "LD_GEMM_STAGES", "LD_GEMM_PROF", "LD_GEMM_TILE_STAGE_CIN", "LD_GEMM_ALIGN", "LD_GEMM_RINGS", "LD_GEMM_DBG"):
         os.environ.pop(k, None)
     os.environ.update(env)
-    eng = Engine(0)
+    eng = Engine(0, chunk_rows=chunk_rows)
     eng.load_state_dict(synth.synthetic_state_dict())
     T = int(minutes * 6000)
     feats = torch.randn(T, 44, device="cuda") * 3 - 4
@@ -53,4 +53,10 @@ def run(label, env, minutes, detail=False):
 if __name__ == "__main__":
     minutes = float(sys.argv[1]) if len(sys.argv) > 1 else 10.0
     run("default", {"LD_GEMM_PROF": "1"}, minutes, detail=True)
-    run("one ring", {"LD_GEMM_RINGS": "1"}, minutes)
+    if len(sys.argv) > 2 and sys.argv[2] == "dbg":
+        run("one group loaded per tile (garbage results)", {"LD_GEMM_PROF": "1", "LD_GEMM_DBG": "1"}, minutes, detail=True)
+    elif len(sys.argv) > 2 and sys.argv[2] == "chunks":
+        for c in (2048, 4096, 8192, 16384, 65536):
+            run(f"chunk_rows={c}", {}, minutes, detail=(c == 4096), chunk_rows=c)
+    else:
+        run("one ring", {"LD_GEMM_RINGS": "1"}, minutes)
