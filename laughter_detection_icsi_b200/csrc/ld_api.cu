@@ -284,9 +284,10 @@ int64_t ld_gemm_program_json(const ld_config* cfg, char* buf, int64_t cap) {
                 for (int g = 0; g < job.n_groups; ++g)
                     s += (g ? ",[" : "[") + std::to_string(plane_of(job.groups[g].src)) + "," + std::to_string(job.groups[g].shift) + "]";
                 s += "],\"taps\":[";
+                const uint4* tapw = L.job_tapw(j);
                 for (int t = 0; t < job.n_taps; ++t)
-                    s += (t ? ",[" : "[") + std::to_string(job.tapw[t].x) + "," + std::to_string(job.tapw[t].y) + "," +
-                         std::to_string(job.tapw[t].z) + "," + std::to_string(job.tapw[t].w) + "]";
+                    s += (t ? ",[" : "[") + std::to_string(tapw[t].x) + "," + std::to_string(tapw[t].y) + "," +
+                         std::to_string(tapw[t].z) + "," + std::to_string(tapw[t].w) + "]";
                 s += "]}";
             }
             s += "]}";

@@ -42,6 +42,8 @@ constexpr int kEpiWarps = 8;      // epilogue warps: two per TMEM lane quadrant,
 constexpr int kGemmThreads = 32 * (kProducers + kIssuers + kEpiWarps);
 constexpr int kAccStages = kIssuers;  // barrier slots of the TMEM accumulator ring
 constexpr int kMaxStages = 16;
+constexpr int kTapBatch = 8;      // taps an issuer warp reads from the job table at a time
+static_assert(kMaxTaps % kTapBatch == 0, "the tap table is read in whole batches");
 
 // Optional per-launch cycle counters (GemmLaunch::prof), summed over CTAs:
 //   0 producer: waiting for a free smem stage      1 MMA warp: waiting for operands      2 MMA warp: waiting for a free accumulator
@@ -89,7 +91,9 @@ template <int CIN, int COUT, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int warp = threadIdx.x >> 5;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform, and everything the issuing thread derives
+    // from it and from the kernel parameters stays on the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     constexpr int kChunks = CIN / 8;   // 16-byte channel chunks per pixel
     constexpr int kSteps = CIN / 16;   // MMAs (K = 16) per tap
@@ -200,17 +204,18 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
             const int p0 = tw.mt * kTileM;
             const int n_groups = job.n_groups;
             for (int g0 = 0; g0 < n_groups; g0 += gps) {
-                const int ng = L.dbg == 1 ? 1 : min(gps, n_groups - g0);
+                const int ng = min(gps, n_groups - g0);
+                const int n_copies = (L.dbg & 1) ? 1 : ng * kChunks;   // (dbg bit 0: timing experiment, one copy per stage)
                 const uint32_t full = bar_full + 8 * (ring0 + stage);
                 if (lane == 0) {
                     const long long t0 = profiling ? clock64() : 0;
                     mbar_wait(bar_empty + 8 * (ring0 + stage), phase ^ 1);
                     if (profiling) c_wait += clock64() - t0;
-                    mbar_expect_tx(full, box_bytes * ng);
+                    mbar_expect_tx(full, lbo_a * n_copies);
                 }
                 __syncwarp();
                 const uint32_t dst0 = stage_addr0 + (ring0 + stage) * lay.stage_bytes;
-                for (int c = lane; c < ng * kChunks; c += 32) {   // one contiguous bulk copy per channel chunk of a group
+                for (int c = lane; c < n_copies; c += 32) {   // one contiguous bulk copy per channel chunk of a group
                     const int g = c / kChunks, kc = c - g * kChunks;
                     const GemmGroup& grp = job.groups[g0 + g];
                     bulk_g2s(dst0 + g * box_bytes + kc * lbo_a, grp.src + static_cast<long long>(p0 + grp.shift) * 8 + kc * grp.kc_stride,
@@ -232,7 +237,6 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
         const uint32_t a_kstep = 2u * static_cast<uint32_t>(ext_alloc);   // two channel chunks per K = 16
         const uint32_t w16 = w_addr >> 4;
         const uint32_t stage16 = lay.stage_bytes >> 4;
-        const bool leader = elect_one();
         mbar_wait(bar_w, 0);
         // issuer iw drains ring iw % n_rings together with the ring's other issuers: they alternate its tiles, the partners'
         // tiles are skipped by advancing the ring position by their stage count
@@ -242,69 +246,72 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
         const int next_issuer = ring + n_rings * ((slot + 1) % ipr);
         const int ring_n = n_stages / n_rings;
         const int ring0 = ring * ring_n;
-        int stage = 0;
-        uint32_t phase = 0;
-        auto advance = [&](int n) {
-            stage += n;
-            while (stage >= ring_n) { stage -= ring_n; phase ^= 1; }
-        };
-        const int acc = iw;
-        uint32_t acc_phase = 0;
-        // "full" barriers are parity-tracked, so a warp must never wait on a stage more than one fill ahead: the issuers of
-        // a ring take turns -- one starts waiting for operands only after the other has seen its last stage
-        uint32_t turn_phase = 0;
+        // The whole warp runs the loop converged -- every value below is warp-uniform, so the compiler keeps the tap words,
+        // the descriptor arithmetic and the MMA operands in uniform registers -- and only the elected lane issues.
+        const bool leader = elect_one();
+        const bool mma_on = leader && !(L.dbg & 2);   // (dbg bit 1: timing experiment, everything but the MMAs themselves)
         long long c_full = 0, c_acc = 0, c_issue = 0;
-        TileWalk tw(blockIdx.x + ring * gridDim.x, n_rings * gridDim.x, n_jobs);
-        for (int it = ring, k = 0; it < my_tiles && iw < n_issuers; it += n_rings, ++k, tw.next()) {
-            const GemmJob& job = s_jobs[tw.job];
-            if ((k % ipr) != slot) {
-                advance(job.n_stages);
-                continue;
-            }
-            const int n_taps = job.n_taps;
-            long long t0 = profiling ? clock64() : 0;
-            if (k > 0) {
-                mbar_wait(bar_turn + 8 * iw, turn_phase);
-                turn_phase ^= 1;
-            }
-            mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
-            if (profiling) { const long long t1 = clock64(); c_acc += t1 - t0; t0 = t1; }
-            tc_fence_after();
+        if (iw < n_issuers) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int acc = iw;
+            uint32_t acc_phase = 0;
+            // "full" barriers are parity-tracked, so a warp must never wait on a stage more than one fill ahead: the issuers
+            // of a ring take turns -- one starts waiting for operands only after the other has seen its last stage
+            uint32_t turn_phase = 0;
             const uint32_t d_tmem = tmem_base + acc * (kTmemCols / n_issuers);
-            uint32_t a_stage = 0;
-#pragma unroll 2
-            for (int t = 0; t < n_taps; ++t) {
-                const uint4 w = job.tapw[t];
-                if (w.x & kTapFirst) {
-                    mbar_wait(bar_full + 8 * (ring0 + stage), phase);
-                    if (profiling) { const long long t1 = clock64(); c_full += t1 - t0; t0 = t1; }
-                    tc_fence_after();
-                    a_stage = a_lo0 | ((stage_addr0 >> 4) + (ring0 + stage) * stage16);
-                    if ((w.x & kTapPass) && lane == 0) mbar_arrive(bar_turn + 8 * next_issuer);
+            TileWalk tw(blockIdx.x + ring * gridDim.x, n_rings * gridDim.x, n_jobs);
+            for (int it = ring, k = 0; it < my_tiles; it += n_rings, ++k, tw.next()) {
+                const GemmJobTaps jt = L.job_taps[tw.job];
+                if ((k % ipr) != slot) {
+                    stage += jt.n_stages;
+                    while (stage >= ring_n) { stage -= ring_n; phase ^= 1; }
+                    continue;
                 }
-                const uint32_t a_lo = a_stage + (w.x & 0x3FFFu);
-                const uint32_t b_lo = w.y + w16;
-                const uint32_t b_kstep = w.y >> 15;   // two channel chunks per K = 16: 2 * LBO
-                const uint32_t d = d_tmem + w.z;
-                const uint32_t idesc = idesc0 | w.w;
+                long long t0c = profiling ? clock64() : 0;
+                if (k > 0) {
+                    mbar_wait(bar_turn + 8 * iw, turn_phase);
+                    turn_phase ^= 1;
+                }
+                mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+                if (profiling) { const long long t1 = clock64(); c_acc += t1 - t0c; t0c = t1; }
+                tc_fence_after();
+                uint32_t a_stage = 0;
+                const int t_end = jt.tap0 + jt.n_taps;
+                for (int t = jt.tap0; t < t_end; ++t) {
+                    const uint4 w = L.taps[t];
+                    if (w.x & kTapFirst) {
+                        mbar_wait(bar_full + 8 * (ring0 + stage), phase);
+                        if (profiling) { const long long t1 = clock64(); c_full += t1 - t0c; t0c = t1; }
+                        tc_fence_after();
+                        a_stage = a_lo0 | ((stage_addr0 >> 4) + (ring0 + stage) * stage16);
+                        if ((w.x & kTapPass) && lane == 0) mbar_arrive(bar_turn + 8 * next_issuer);
+                    }
+                    const uint32_t a_lo = a_stage + (w.x & 0x3FFFu);
+                    const uint32_t b_lo = w.y + w16;
+                    const uint32_t b_kstep = w.y >> 15;   // two channel chunks per K = 16: 2 * LBO
+                    const uint32_t d = d_tmem + w.z;
+                    const uint32_t idesc = idesc0 | w.w;
 #pragma unroll
-                for (int ks = 0; ks < kSteps; ++ks)
-                    umma_f16_ss_pred(d, umma_pack_desc(a_lo + ks * a_kstep, desc_hi), umma_pack_desc(b_lo + ks * b_kstep, desc_hi),
-                                     idesc, 1u, leader);
-                if (w.x & kTapLast) {
-                    umma_commit_pred(bar_empty + 8 * (ring0 + stage), leader);  // frees the smem stage when these MMAs retire
-                    if (profiling) { const long long t1 = clock64(); c_issue += t1 - t0; t0 = t1; }
-                    advance(1);
+                    for (int ks = 0; ks < kSteps; ++ks)
+                        umma_f16_ss_pred(d, umma_pack_desc(a_lo + ks * a_kstep, desc_hi), umma_pack_desc(b_lo + ks * b_kstep, desc_hi), idesc, 1u,
+                                         mma_on);
+                    if (w.x & kTapLast) {
+                        umma_commit_pred(bar_empty + 8 * (ring0 + stage), leader);  // frees the smem stage when these MMAs retire
+                        if (profiling) { const long long t1 = clock64(); c_issue += t1 - t0c; t0c = t1; }
+                        if (++stage == ring_n) { stage = 0; phase ^= 1; }
+                    }
                 }
+                umma_commit_pred(bar_acc_full + 8 * acc, leader);
+                acc_phase ^= 1;
             }
-            umma_commit_pred(bar_acc_full + 8 * acc, leader);
-            acc_phase ^= 1;
+            if (profiling && iw == 0 && lane == 0) {
+                atomicAdd(prof + PROF_MMA_WAIT_FULL, static_cast<unsigned long long>(c_full));
+                atomicAdd(prof + PROF_MMA_WAIT_ACC, static_cast<unsigned long long>(c_acc));
+                atomicAdd(prof + PROF_MMA_ISSUE, static_cast<unsigned long long>(c_issue));
+            }
         }
-        if (profiling && lane == 0 && iw == 0) {
-            atomicAdd(prof + PROF_MMA_WAIT_FULL, static_cast<unsigned long long>(c_full));
-            atomicAdd(prof + PROF_MMA_WAIT_ACC, static_cast<unsigned long long>(c_acc));
-            atomicAdd(prof + PROF_MMA_ISSUE, static_cast<unsigned long long>(c_issue));
-        }
+        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue
         const int q = warp & 3;  // TMEM lane quadrant this warp may read
@@ -337,7 +344,7 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
             const bool inner = locate(p, row, col);
             const bool valid = p < M;
             long long dst_off;   // element offset of this pixel inside an output plane
-            bool odd = false, do_store;
+            bool odd = false, do_store;   // (dbg bit 2: timing experiment without the epilogue's global stores)
             if (out_mode == OUT_PLAIN) {
                 dst_off = static_cast<long long>(p) * 8;
                 do_store = valid;
@@ -347,6 +354,7 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
                 dst_off = (static_cast<long long>(row) * wp2 + (c0 >> 1) + 1) * 8;
                 do_store = valid && inner;
             }
+            if (L.dbg & 4) do_store = false;
             const long long out_kc = job.out_kc_stride;
             const int n_outs = job.n_outs;
             tw.next();
@@ -359,9 +367,14 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
             for (int o = 0; o < n_outs; ++o) {
                 const uint32_t taddr = taddr0 + o * COUT + half * CH;
                 uint32_t v[CH];
-                tmem_ld_cols<CH>(taddr, v);
-                tmem_wait_ld();
-                tmem_zero_cols<CH>(taddr);   // the next tile's MMAs accumulate into zeros
+                if (!(L.dbg & 8)) {   // (dbg bit 3: timing experiment without the TMEM traffic of the epilogue)
+                    tmem_ld_cols<CH>(taddr, v);
+                    tmem_wait_ld();
+                    tmem_zero_cols<CH>(taddr);   // the next tile's MMAs accumulate into zeros
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) v[c] = 0u;
+                }
                 if (o == n_outs - 1) {
                     tmem_wait_st();
                     tc_fence_before();

@@ -43,7 +43,7 @@ bool shares_input(const HostJob& a, const HostJob& b) {
 
 }  // namespace
 
-static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, int max_outs, std::string& err);
+static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, int max_outs, bool pack_all, std::string& err);
 
 // The caller presets L's header (weights, shift, cin, cout, n_wtaps, w_stack, relu, wp, out_mode, wp2, hp, mode, stats, prof).
 bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, std::string& err) {
@@ -55,13 +55,17 @@ bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
     L.n_issuers = L.cout >= 48 ? tune.issuers_wide : tune.issuers_narrow;
     if (L.n_issuers != 2 && L.n_issuers != 4) { err = "2 or 4 MMA issuers"; return false; }
     // the longest chains whose loads and taps fit a job (stride-2 layers merge nothing: their chains stay short)
-    const int max_outs = L.w_stack ? std::max(1, std::min({tune.max_outs, kMaxOuts, kTmemCols / L.n_issuers / L.cout})) : 1;
+    // 1x1 convs (one or two taps per output) share nothing, but several outputs per job still amortise the per-tile costs
+    bool pack_all = true;
+    for (const auto& o : outs) pack_all = pack_all && o.taps.size() <= 2;
+    const int max_outs = (L.w_stack || pack_all) ? std::max(1, std::min({tune.max_outs, kMaxOuts, kTmemCols / L.n_issuers / L.cout})) : 1;
     for (int mo = max_outs; mo >= 1; --mo)
-        if (build_with(L, outs, tune, mo, err)) return true;
+        if (build_with(L, outs, tune, mo, pack_all, err)) return true;
     return false;
 }
 
-static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, const int max_outs, std::string& err) {
+static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, const int max_outs, const bool pack_all,
+                       std::string& err) {
     const int kchunks = L.cin / 8;
     const bool stack = L.w_stack != 0;
 
@@ -69,7 +73,7 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
     std::vector<std::pair<int, int>> parts;  // [first, last) output indices
     for (size_t a = 0; a < outs.size();) {
         size_t b = a + 1;
-        while (max_outs > 1 && b < outs.size() && shares_input(outs[b - 1], outs[b])) ++b;
+        while (max_outs > 1 && b < outs.size() && (pack_all || shares_input(outs[b - 1], outs[b]))) ++b;
         const int n = static_cast<int>(b - a), n_parts = (n + max_outs - 1) / max_outs;
         for (int i = 0; i < n_parts; ++i)
             parts.push_back({static_cast<int>(a) + i * n / n_parts, static_cast<int>(a) + (i + 1) * n / n_parts});
@@ -141,9 +145,11 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
     // ---- 4. the tap program: per group, per pixel offset, runs of adjacent outputs with adjacent weight rows -> one MMA
     const int gps = L.groups_per_stage;
     const uint32_t box16 = static_cast<uint32_t>(L.ext_alloc) * kchunks;
+    int n_launch_taps = 0;
     for (size_t j = 0; j < parts.size(); ++j) {
         GemmJob& job = L.jobs[j];
         std::vector<Tap>& taps = job_taps[j];
+        uint4* tapw = L.taps + n_launch_taps;
         // weight row block of a tap inside its stacked block (ky = 2, 1, 0), or -1 for a stand-alone slab
         auto wrow = [&](const Tap& t) { return (stack && t.wslab < 9) ? 2 - t.wslab / 3 : -1; };
         auto kx_of = [&](const Tap& t) { return (stack && t.wslab < 9) ? t.wslab % 3 : t.wslab; };
@@ -159,7 +165,7 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
                        kx_of(taps[e]) == kx_of(taps[i]) && wrow(taps[e]) >= 0 && taps[e].out == taps[e - 1].out + 1 &&
                        wrow(taps[e]) == wrow(taps[e - 1]) + 1)
                     ++e;
-            if (n >= kMaxTaps) { err = "too many MMA taps in a job"; return false; }
+            if (n >= kMaxTaps || n_launch_taps + n >= kMaxLaunchTaps) { err = "too many MMA taps in a job"; return false; }
             const Tap& t = taps[i];
             const int n_merged = static_cast<int>(e - i);
             const uint32_t a16 = static_cast<uint32_t>(t.group % gps) * box16 + static_cast<uint32_t>(t.off);
@@ -177,16 +183,18 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
             const bool last = e == taps.size() || taps[e].group / gps != stage_of;
             const uint32_t col = static_cast<uint32_t>(t.out) * L.cout, ncols = static_cast<uint32_t>(n_merged) * L.cout;
             if (col + ncols > static_cast<uint32_t>(kTmemCols / L.n_issuers)) { err = "accumulator overflow"; return false; }
-            job.tapw[n].x = a16 | (first ? kTapFirst : 0u) | (last ? kTapLast : 0u);
-            job.tapw[n].y = b16 | (lbo16 << 16);
-            job.tapw[n].z = col;
-            job.tapw[n].w = (ncols >> 3) << 17;
+            tapw[n].x = a16 | (first ? kTapFirst : 0u) | (last ? kTapLast : 0u);
+            tapw[n].y = b16 | (lbo16 << 16);
+            tapw[n].z = col;
+            tapw[n].w = (ncols >> 3) << 17;
             if (first) last_first = n;
             ++n;
             i = e;
         }
-        job.tapw[last_first].x |= kTapPass;
+        tapw[last_first].x |= kTapPass;
         job.n_taps = n;
+        L.job_taps[j] = {static_cast<uint16_t>(n_launch_taps), static_cast<uint16_t>(n), static_cast<uint16_t>(job.n_stages), 0};
+        n_launch_taps += n;
     }
     return true;
 }

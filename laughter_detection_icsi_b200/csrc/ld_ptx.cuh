@@ -132,8 +132,9 @@ __device__ __forceinline__ void umma_f16_ss_pred(uint32_t d_tmem, uint64_t a_des
         "setp.ne.b32 p, %4, 0;\n\t"
         "setp.ne.b32 q, %5, 0;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(issue))
-        : "memory");
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(issue)));
+    // (volatile, but no "memory" clobber: the MMA touches no C++-visible memory; its ordering against the mbarrier waits and
+    //  commits around it -- all volatile asm -- is kept, while plain loads of the next taps may be scheduled across it)
 }
 __device__ __forceinline__ void umma_commit_pred(uint32_t bar, bool issue) {
     asm volatile(

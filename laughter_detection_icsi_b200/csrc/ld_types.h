@@ -21,6 +21,7 @@ namespace ld {
 constexpr int kTileM = 128;      // output pixels per MMA tile (UMMA M)
 constexpr int kMaxGroups = 16;   // distinct smem loads per job
 constexpr int kMaxTaps = 32;     // MMA taps per job
+constexpr int kMaxLaunchTaps = 128;  // MMA taps per launch (all jobs)
 constexpr int kMaxOuts = 8;      // output planes per job (their accumulators sit side by side in TMEM)
 constexpr int kTmemCols = 512;   // accumulator columns per SM, split into n_issuers stages: n_outs * cout <= 512 / n_issuers
 constexpr int kMaxJobs = 16;     // jobs per launch (the planner also splits a layer into launches of at most this many output planes)
@@ -56,17 +57,24 @@ struct GemmOut {
     __half* out0;  // PLAIN: the plane; COLSPLIT: even-column plane
     __half* out1;  // COLSPLIT: odd-column plane
 };
-struct alignas(16) GemmJob {
-    uint4 tapw[kMaxTaps];
+struct alignas(16) GemmJob {          // what the producers and the epilogue need of a job (copied to shared memory)
     GemmGroup groups[kMaxGroups];
     GemmOut outs[kMaxOuts];
     int32_t n_groups, n_taps, n_outs, n_stages;  // n_stages = ceil(n_groups / groups_per_stage)
     int64_t out_kc_stride;
     int64_t pad_;
 };
+struct GemmJobTaps {   // where a job's tap program sits in GemmParams::taps
+    uint16_t tap0, n_taps, n_stages, pad_;
+};
 struct GemmParams {         // the kernel's __grid_constant__ parameter
-    const GemmJob* jobs_dev;  // [n_jobs] in device memory; every CTA copies the table into shared memory (the roles index it
-                              // per tile and per tap: the constant path thrashes on a table of this size)
+    // The tap programs of all jobs, densely packed.  They stay in parameter (constant) space on purpose: the issuing thread
+    // indexes them with warp-uniform values, so the loads, the descriptor arithmetic and the tcgen05.mma operands all live
+    // in uniform registers (a table read through shared memory lands in vector registers and costs ~7 R2UR per MMA).
+    uint4 taps[kMaxLaunchTaps];
+    GemmJobTaps job_taps[kMaxJobs];
+    const GemmJob* jobs_dev;  // [n_jobs] in device memory; every CTA copies the table into shared memory (producers and
+                              // epilogue index it per lane; the constant path would thrash on it)
     const __half* weights;  // [n_wtaps][cin/8][cout][8] fp16, BatchNorm scale folded in
     const float* shift;     // [cout] folded BatchNorm shift (+ conv bias)
     int32_t n_jobs, cin, cout, n_wtaps;
@@ -77,7 +85,8 @@ struct GemmParams {         // the kernel's __grid_constant__ parameter
     int32_t groups_per_stage;  // consecutive groups of a job that share one smem stage (one barrier round trip)
     uint32_t wp_magic;  // floor(2^32 / wp) + 1: row = umulhi(pixel, wp_magic)
     int32_t w_stack;    // 1: 3x3 weights are re-stacked in smem as [kx][cin/8][ky = 2,1,0][cout][8] (slab 9, if any, stays a slab)
-    int32_t dbg;        // timing experiments only (LD_GEMM_DBG): 1 = producers copy one group per stage (results are garbage)
+    int32_t dbg;        // timing experiments only (LD_GEMM_DBG, results are garbage): bit 0 one copy per smem stage, bit 1 no MMAs,
+                        // bit 2 no global stores, bit 3 no TMEM reads/clears in the epilogue
     int32_t n_issuers;  // MMA-issuing warps = accumulator stages (2: 256 columns each, 4: 128 columns each)
     int32_t n_rings;    // 2: two producer/issuer pipelines over half the stages each; 1: a single ring
     int32_t mode;       // 0: inference (fp16, shift + ReLU epilogue); 1: training (bf16, raw output + channel statistics)
@@ -86,6 +95,7 @@ struct GemmParams {         // the kernel's __grid_constant__ parameter
 };
 struct GemmLaunch : GemmParams {   // host side: the parameters plus the job table gemm_build_launch fills;
     GemmJob jobs[kMaxJobs];        // launch_gemm_taps uploads it on first use (jobs_dev), gemm_release frees it
+    const uint4* job_tapw(int j) const { return taps + job_taps[j].tap0; }
 };
 
 // ---- host-side plan (plane ids instead of pointers) ----

@@ -54,7 +54,9 @@ if __name__ == "__main__":
     minutes = float(sys.argv[1]) if len(sys.argv) > 1 else 10.0
     run("default", {"LD_GEMM_PROF": "1"}, minutes, detail=True)
     if len(sys.argv) > 2 and sys.argv[2] == "dbg":
-        run("one group loaded per tile (garbage results)", {"LD_GEMM_PROF": "1", "LD_GEMM_DBG": "1"}, minutes, detail=True)
+        for bits, what in ((2, "no MMAs"), (3, "no MMAs, one copy per stage"), (6, "no MMAs, no stores"), (14, "no MMAs, no stores, no TMEM reads"),
+                           (15, "barrier skeleton only"), (4, "no stores"), (1, "one copy per stage")):
+            run(f"LD_GEMM_DBG={bits}: {what} (garbage results)", {"LD_GEMM_PROF": "1", "LD_GEMM_DBG": str(bits)}, minutes, detail=bits in (15, 14))
     elif len(sys.argv) > 2 and sys.argv[2] == "chunks":
         for c in (2048, 4096, 8192, 16384, 65536):
             run(f"chunk_rows={c}", {}, minutes, detail=(c == 4096), chunk_rows=c)
