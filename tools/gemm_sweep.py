@@ -14,7 +14,8 @@ NAMES = ["prod_wait", "mma_wait_full", "mma_wait_acc", "mma_issue", "epi_wait", 
 
 
 def run(label, env, minutes, detail=False, chunk_rows=0):
-    for k in ("LD_GEMM_LOADER", "LD_GEMM_SPAN", "LD_GEMM_STAGES", "LD_GEMM_PROF", "LD_GEMM_TILE_STAGE_CIN", "LD_GEMM_ALIGN", "LD_GEMM_RINGS", "LD_GEMM_DBG"):
+    for k in ("LD_GEMM_SPAN", "LD_GEMM_STAGES", "LD_GEMM_PROF", "LD_GEMM_STAGE_BYTES", "LD_GEMM_MAX_OUTS", "LD_GEMM_RINGS", "LD_GEMM_DBG",
+              "LD_GEMM_ISSUERS_WIDE", "LD_GEMM_ISSUERS_NARROW"):
         os.environ.pop(k, None)
     os.environ.update(env)
     eng = Engine(0, chunk_rows=chunk_rows)
@@ -57,6 +58,10 @@ if __name__ == "__main__":
         for bits, what in ((2, "no MMAs"), (3, "no MMAs, one copy per stage"), (6, "no MMAs, no stores"), (14, "no MMAs, no stores, no TMEM reads"),
                            (15, "barrier skeleton only"), (4, "no stores"), (1, "one copy per stage")):
             run(f"LD_GEMM_DBG={bits}: {what} (garbage results)", {"LD_GEMM_PROF": "1", "LD_GEMM_DBG": str(bits)}, minutes, detail=bits in (15, 14))
+    elif len(sys.argv) > 2 and sys.argv[2] == "knobs":
+        for env in ({"LD_GEMM_ISSUERS_WIDE": "4"}, {"LD_GEMM_ISSUERS_NARROW": "2"}, {"LD_GEMM_STAGE_BYTES": "9000"},
+                    {"LD_GEMM_STAGE_BYTES": "36000"}, {"LD_GEMM_MAX_OUTS": "2"}, {"LD_GEMM_MAX_OUTS": "3"}, {"LD_GEMM_SPAN": "0"}):
+            run(" ".join(f"{k}={v}" for k, v in env.items()), dict(env, LD_GEMM_PROF="1"), minutes, detail=True)
     elif len(sys.argv) > 2 and sys.argv[2] == "chunks":
         for c in (2048, 4096, 8192, 16384, 65536):
             run(f"chunk_rows={c}", {}, minutes, detail=(c == 4096), chunk_rows=c)
