@@ -35,6 +35,9 @@ WANT = {
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram % of peak",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor pipe active %",
     "sm__inst_executed_pipe_tensor_op_hmma.avg.pct_of_peak_sustained_active": "tensor hmma %",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active": "tensor hmma pipe active %",
+    "l1tex__m_xbar2l1tex_read_bytes.sum": "L2 -> SM bytes",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed": "L2 throughput %",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "SM throughput %",
     "lts__t_sector_hit_rate.pct": "L2 hit rate %",
     "launch__registers_per_thread": "registers/thread",
