@@ -207,98 +207,123 @@ __device__ __forceinline__ void bn_coef_setup(BnCoef& s, const BnRef& bn, int C)
         s.ya[c] = bn.gamma[c] * inv; s.yb[c] = fmaf(-mean * inv, bn.gamma[c], bn.beta[c]);
     }
 }
-__device__ __forceinline__ void decode_item(long long i, int chunks, int W, int H, int& kc, int& b, int& r0, int& c0) {
-    kc = static_cast<int>(i % chunks);
-    const long long pix = i / chunks;
-    c0 = static_cast<int>(pix % W);
-    const long long rest = pix / W;
-    r0 = static_cast<int>(rest % H);
-    b = static_cast<int>(rest / H);
+// Work split of the element-wise BatchNorm kernels: warp w of the grid owns channel chunk w % chunks for good and walks
+// groups of 32 consecutive real pixels (a 512-byte contiguous run of every plane it touches) with stride n_warps / chunks,
+// so the per-channel coefficients sit in registers and the reductions stay in registers until the end.  All index math is
+// 32-bit (B * H * W <= 1024 * 100 * 44).
+struct EwWalk {
+    int kc, lane, P, W, H;
+    unsigned group, group_stride, n_groups, magic_w, magic_h;
+    __device__ EwWalk(int chunks, int B, int H_, int W_) : W(W_), H(H_) {
+        const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+        lane = threadIdx.x & 31;
+        kc = static_cast<int>(warp % chunks);
+        group = warp / chunks;
+        group_stride = n_warps / chunks;   // the launchers keep n_warps a multiple of 8 >= chunks
+        P = B * H * W;
+        n_groups = (static_cast<unsigned>(P) + 31u) / 32u;
+        // n / d = umulhi(n, floor(2^32 / d) + 1), exact for n * d < 2^32 (here n < 2^23, d <= 100)
+        magic_w = 0xFFFFFFFFu / static_cast<unsigned>(W) + 1u;
+        magic_h = 0xFFFFFFFFu / static_cast<unsigned>(H) + 1u;
+    }
+    __device__ bool pixel(unsigned g, int& b, int& r0, int& c0) const {
+        const unsigned pix = g * 32u + lane;
+        const unsigned row = __umulhi(pix, magic_w);
+        c0 = static_cast<int>(pix - row * W);
+        b = static_cast<int>(__umulhi(row, magic_h));
+        r0 = static_cast<int>(row - b * H);
+        return pix < static_cast<unsigned>(P);
+    }
+};
+// Element offset of real pixel (b, r, c) in a plain plane / in a quad plane set (32-bit pixel index: planes stay below 2^28 pixels).
+__device__ __forceinline__ long long plain_off(const TPlane& t, int b, int r, int c) {
+    return static_cast<long long>((b * t.hp + 1 + r) * t.wp + 1 + c) * 8;
+}
+__device__ __forceinline__ long long any_off(const TPlane& t, int b, int r, int c, long long plain, int& which) {
+    if (!t.quad) { which = 0; return plain; }
+    which = (r & 1) * 2 + (c & 1);
+    return static_cast<long long>((b * t.hp + 1 + (r >> 1)) * t.wp + 1 + (c >> 1)) * 8;
 }
 
-// y = act( bn(z) [+ res] ),  res = plane value (res_mode 1) or bn_s(zs) (res_mode 2).  Grid-stride over
-// (real pixel, 8-channel chunk) items.  z and res planes are plain; y may be plain or quad.
+// y = act( bn(z) [+ res] ),  res = plane value (res_mode 1) or bn_s(zs) (res_mode 2).  z and res planes are plain; y may be
+// plain or quad.
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(TPlane z, BnRef bn, int relu, int res_mode, TPlane res, BnRef bn_res, TPlane y, int B) {
     __shared__ BnCoef s, sr;
-    const int C = z.C, H = z.H, W = z.W, chunks = C / 8;
+    const int C = z.C;
     bn_coef_setup(s, bn, C);
     if (res_mode == 2) bn_coef_setup(sr, bn_res, C);
     __syncthreads();
-    const long long n = static_cast<long long>(B) * H * W * chunks;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        int kc, b, r0, c0, which;
-        decode_item(i, chunks, W, H, kc, b, r0, c0);
+    const EwWalk w(C / 8, B, z.H, z.W);
+    const int kc = w.kc;
+    float ya[8], yb[8], ra[8], rb[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        ya[e] = s.ya[kc * 8 + e]; yb[e] = s.yb[kc * 8 + e];
+        ra[e] = res_mode == 2 ? sr.ya[kc * 8 + e] : 1.f; rb[e] = res_mode == 2 ? sr.yb[kc * 8 + e] : 0.f;
+    }
+    for (unsigned g = w.group; g < w.n_groups; g += w.group_stride) {
+        int b, r0, c0, which;
+        if (!w.pixel(g, b, r0, c0)) continue;
         float v[8], o[8], rv[8];
-        load8(z.base[0] + kc * z.kc_stride + tpix(z, b, r0, c0, which) * 8, v);
-        if (res_mode != 0) load8(res.base[0] + kc * res.kc_stride + tpix(res, b, r0, c0, which) * 8, rv);
+        const long long pz = plain_off(z, b, r0, c0);   // z and res are plain planes of the same geometry
+        load8(z.base[0] + kc * z.kc_stride + pz, v);
+        if (res_mode != 0) load8(res.base[0] + kc * res.kc_stride + pz, rv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int c = kc * 8 + e;
-            float a = fmaf(v[e], s.ya[c], s.yb[c]);
-            if (res_mode == 1) a += rv[e];
-            else if (res_mode == 2) a += fmaf(rv[e], sr.ya[c], sr.yb[c]);
+            float a = fmaf(v[e], ya[e], yb[e]);
+            if (res_mode != 0) a += fmaf(rv[e], ra[e], rb[e]);
             o[e] = relu ? fmaxf(a, 0.f) : a;
         }
-        const long long py = tpix(y, b, r0, c0, which);
-        store8(y.base[which] + kc * y.kc_stride + py * 8, o);
+        const long long py = any_off(y, b, r0, c0, pz, which);
+        store8(y.base[which] + kc * y.kc_stride + py, o);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ BatchNorm backward
-// g = dy * [y > 0] (relu) ; reductions sum g, sum g*xhat per channel.  A warp covers 32 consecutive real pixels of ONE chunk.
+// g = dy * [y > 0] (relu) ; reductions sum g, sum g*xhat per channel.
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, int B, float* __restrict__ sums /*[2C]*/) {
     __shared__ float s_acc[128];
     __shared__ BnCoef s;
-    const int C = z.C, H = z.H, W = z.W, chunks = C / 8;
+    const int C = z.C;
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
     bn_coef_setup(s, bn, C);
     __syncthreads();
-    const long long P = static_cast<long long>(B) * H * W;
-    const long long groups = (P + 31) / 32;
-    const int lane = threadIdx.x & 31;
-    const long long warp_id = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-    for (long long wk = warp_id; wk < groups * chunks; wk += n_warps) {
-        const int kc = static_cast<int>(wk % chunks);
-        const long long pix = (wk / chunks) * 32 + lane;
-        float sg[8], sx[8];
+    const EwWalk w(C / 8, B, z.H, z.W);
+    const int kc = w.kc;
+    float xa[8], xb[8], sg[8], sx[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { sg[e] = 0.f; sx[e] = 0.f; }
-        if (pix < P) {
-            const int c0 = static_cast<int>(pix % W), r0 = static_cast<int>((pix / W) % H), b = static_cast<int>(pix / (static_cast<long long>(W) * H));
-            int which;
-            float g[8], zz[8], yy[8];
-            const long long pd = tpix(dy, b, r0, c0, which);
-            load8(dy.base[which] + kc * dy.kc_stride + pd * 8, g);
-            if (relu) {
-                const long long py = tpix(y, b, r0, c0, which);
-                load8(y.base[which] + kc * y.kc_stride + py * 8, yy);
-            }
-            load8(z.base[0] + kc * z.kc_stride + tpix(z, b, r0, c0, which) * 8, zz);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int c = kc * 8 + e;
-                const float ge = (relu && !(yy[e] > 0.f)) ? 0.f : g[e];
-                sg[e] = ge;
-                sx[e] = ge * fmaf(zz[e], s.xa[c], s.xb[c]);
-            }
-        }
+    for (int e = 0; e < 8; ++e) { xa[e] = s.xa[kc * 8 + e]; xb[e] = s.xb[kc * 8 + e]; sg[e] = 0.f; sx[e] = 0.f; }
+    for (unsigned g = w.group; g < w.n_groups; g += w.group_stride) {
+        int b, r0, c0, which;
+        if (!w.pixel(g, b, r0, c0)) continue;
+        float gg[8], zz[8], yy[8];
+        const long long pz = plain_off(z, b, r0, c0);   // dy and y share one geometry (plain like z, or quad)
+        const long long pd = any_off(dy, b, r0, c0, pz, which);
+        load8(dy.base[which] + kc * dy.kc_stride + pd, gg);
+        if (relu) load8(y.base[which] + kc * y.kc_stride + pd, yy);
+        load8(z.base[0] + kc * z.kc_stride + pz, zz);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                sg[e] += __shfl_xor_sync(0xffffffffu, sg[e], o);
-                sx[e] += __shfl_xor_sync(0xffffffffu, sx[e], o);
-            }
+            const float ge = (relu && !(yy[e] > 0.f)) ? 0.f : gg[e];
+            sg[e] += ge;
+            sx[e] = fmaf(ge, fmaf(zz[e], xa[e], xb[e]), sx[e]);
         }
-        if (lane == 0) {
+    }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                atomicAdd(s_acc + kc * 8 + e, sg[e]);
-                atomicAdd(s_acc + C + kc * 8 + e, sx[e]);
-            }
+    for (int e = 0; e < 8; ++e) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            sg[e] += __shfl_xor_sync(0xffffffffu, sg[e], o);
+            sx[e] += __shfl_xor_sync(0xffffffffu, sx[e], o);
+        }
+    }
+    if (w.lane == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            atomicAdd(s_acc + kc * 8 + e, sg[e]);
+            atomicAdd(s_acc + C + kc * 8 + e, sx[e]);
         }
     }
     __syncthreads();
@@ -311,36 +336,39 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, const float* __restrict__ sums, int B, TPlane dz, int write_g,
                     TPlane g_out, float* __restrict__ dgamma, float* __restrict__ dbeta) {
     __shared__ BnCoef s;
-    __shared__ float s_c1[64], s_c2[64];   // mean(g), mean(g xhat)
-    const int C = z.C, H = z.H, W = z.W, chunks = C / 8;
+    const int C = z.C;
     bn_coef_setup(s, bn, C);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) { s_c1[c] = sums[c] * bn.inv_n; s_c2[c] = sums[C + c] * bn.inv_n; }
     if (blockIdx.x == 0 && threadIdx.x < C) {
         dgamma[threadIdx.x] = sums[C + threadIdx.x];
         dbeta[threadIdx.x] = sums[threadIdx.x];
     }
     __syncthreads();
-    const long long n = static_cast<long long>(B) * H * W * chunks;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        int kc, b, r0, c0, which;
-        decode_item(i, chunks, W, H, kc, b, r0, c0);
-        float g[8], zz[8], yy[8], o[8];
-        const long long pd = tpix(dy, b, r0, c0, which);
-        load8(dy.base[which] + kc * dy.kc_stride + pd * 8, g);
-        if (relu) {
-            const long long py = tpix(y, b, r0, c0, which);
-            load8(y.base[which] + kc * y.kc_stride + py * 8, yy);
-        }
-        load8(z.base[0] + kc * z.kc_stride + tpix(z, b, r0, c0, which) * 8, zz);
+    const EwWalk w(C / 8, B, z.H, z.W);
+    const int kc = w.kc;
+    float xa[8], xb[8], ya[8], c1[8], c2[8];   // c1 = mean(g), c2 = mean(g xhat)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = kc * 8 + e;
+        xa[e] = s.xa[c]; xb[e] = s.xb[c]; ya[e] = s.ya[c];
+        c1[e] = sums[c] * bn.inv_n; c2[e] = sums[C + c] * bn.inv_n;
+    }
+    for (unsigned g = w.group; g < w.n_groups; g += w.group_stride) {
+        int b, r0, c0, which;
+        if (!w.pixel(g, b, r0, c0)) continue;
+        float gg[8], zz[8], yy[8], o[8];
+        const long long pz = plain_off(z, b, r0, c0);   // dy and y share one geometry (plain like z, or quad); dz, g_out are plain
+        const long long pd = any_off(dy, b, r0, c0, pz, which);
+        load8(dy.base[which] + kc * dy.kc_stride + pd, gg);
+        if (relu) load8(y.base[which] + kc * y.kc_stride + pd, yy);
+        load8(z.base[0] + kc * z.kc_stride + pz, zz);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int c = kc * 8 + e;
-            if (relu && !(yy[e] > 0.f)) g[e] = 0.f;
-            const float xh = fmaf(zz[e], s.xa[c], s.xb[c]);
-            o[e] = s.ya[c] * (g[e] - s_c1[c] - xh * s_c2[c]);
+            if (relu && !(yy[e] > 0.f)) gg[e] = 0.f;
+            const float xh = fmaf(zz[e], xa[e], xb[e]);
+            o[e] = ya[e] * (gg[e] - c1[e] - xh * c2[e]);
         }
-        store8(dz.base[0] + kc * dz.kc_stride + tpix(dz, b, r0, c0, which) * 8, o);
-        if (write_g) store8(g_out.base[0] + kc * g_out.kc_stride + tpix(g_out, b, r0, c0, which) * 8, g);
+        store8(dz.base[0] + kc * dz.kc_stride + pz, o);
+        if (write_g) store8(g_out.base[0] + kc * g_out.kc_stride + pz, gg);
     }
 }
 
