@@ -127,6 +127,22 @@ def plan_json(cfg=None):
     return json.loads(buf.value.decode())
 
 
+def plan_plane_bytes_per_row(cfg=None):
+    """Activation bytes the conv launches of the streaming plan move per sequence row if every plane crosses HBM once per
+    launch that touches it: for each launch its distinct input, residual and output planes (fp16, wp x C per row).  This is
+    the algorithmic traffic figure behind bench.py's HBM roofline."""
+    plan = plan_json(cfg)
+    size = {p["id"]: 2 * p["wp"] * p["C"] for p in plan["planes"]}
+    total = 0
+    for c in plan["convs"]:
+        touched = set()
+        for job in c["jobs"]:
+            touched.update(p for p, _, _ in job["taps"])
+            touched.update(x for x in (job["res"], job["out0"], job.get("out1", -1)) if x >= 0)
+        total += sum(size[i] for i in touched)
+    return float(total)
+
+
 def gemm_program_json(cfg=None):
     """The tensor-core tap programs of the plan's conv launches as a dict (host builder only; runs without a GPU)."""
     lib = load_library()

@@ -164,7 +164,8 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
         // ------------------------------------------------------------------ producers
         if (warp == 0) {
             // weights -> smem.  Stacked 3x3 layout: [kx][cin/8][ky = 2, 1, 0][cout][8], so that the rows of the outputs an
-            // input row feeds (ky = 2 for the row above, 1 for its own, 0 for the row below) are adjacent along N.
+            // input row feeds (ky = 2 for the row above, 1 for its own, 0 for the row below) are adjacent along N
+            // (stride-2 convs: ky = 2, 0, 1 -- an odd input row feeds ky = 2 of one output and ky = 0 of the next).
             constexpr uint32_t tap_bytes = static_cast<uint32_t>(CIN) * COUT * 2, row_bytes = COUT * 16u;
             const uint32_t jobs_bytes = static_cast<uint32_t>(n_jobs) * static_cast<uint32_t>(sizeof(GemmJob));
             if (lane == 0) {
@@ -176,7 +177,7 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
             if (L.w_stack) {
                 for (int c = lane; c < 9 * kChunks; c += 32) {
                     const int slab = c / kChunks, kc = c - slab * kChunks, ky = slab / 3, kx = slab - ky * 3;
-                    bulk_g2s(w_addr + ((kx * kChunks + kc) * 3 + (2 - ky)) * row_bytes, wsrc + static_cast<size_t>(c) * row_bytes,
+                    bulk_g2s(w_addr + ((kx * kChunks + kc) * 3 + w_stack_row(L.w_stack, ky)) * row_bytes, wsrc + static_cast<size_t>(c) * row_bytes,
                              row_bytes, bar_w);
                 }
                 for (int t = 9 + lane; t < n_wtaps; t += 32)

@@ -59,9 +59,23 @@ bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
     bool pack_all = true;
     for (const auto& o : outs) pack_all = pack_all && o.taps.size() <= 2;
     const int max_outs = (L.w_stack || pack_all) ? std::max(1, std::min({tune.max_outs, kMaxOuts, kTmemCols / L.n_issuers / L.cout})) : 1;
-    for (int mo = max_outs; mo >= 1; --mo)
-        if (build_with(L, outs, tune, mo, pack_all, err)) return true;
-    return false;
+    auto build = [&]() {
+        for (int mo = max_outs; mo >= 1; --mo)
+            if (build_with(L, outs, tune, mo, pack_all, err)) return true;
+        return false;
+    };
+    if (!L.w_stack) return build();
+    // two stacking orders of the weight rows: ky = 2,1,0 merges the three outputs a stride-1 input row feeds, ky = 2,0,1 the
+    // two outputs (ky = 2 of row h, ky = 0 of row h + 1) an odd input row of a stride-2 conv feeds; keep the shorter program
+    int n_taps[3] = {0, 1 << 30, 1 << 30};
+    for (int order = 1; order <= 2; ++order) {
+        L.w_stack = order;
+        if (!build()) continue;
+        n_taps[order] = 0;
+        for (int j = 0; j < L.n_jobs; ++j) n_taps[order] += L.job_taps[j].n_taps;
+    }
+    L.w_stack = n_taps[2] < n_taps[1] ? 2 : 1;
+    return build();
 }
 
 static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, const int max_outs, const bool pack_all,
@@ -150,8 +164,8 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
         GemmJob& job = L.jobs[j];
         std::vector<Tap>& taps = job_taps[j];
         uint4* tapw = L.taps + n_launch_taps;
-        // weight row block of a tap inside its stacked block (ky = 2, 1, 0), or -1 for a stand-alone slab
-        auto wrow = [&](const Tap& t) { return (stack && t.wslab < 9) ? 2 - t.wslab / 3 : -1; };
+        // weight row block of a tap inside its stacked block (ky = 2, 1, 0 or ky = 2, 0, 1), or -1 for a stand-alone slab
+        auto wrow = [&](const Tap& t) { return (stack && t.wslab < 9) ? w_stack_row(L.w_stack, t.wslab / 3) : -1; };
         auto kx_of = [&](const Tap& t) { return (stack && t.wslab < 9) ? t.wslab % 3 : t.wslab; };
         std::sort(taps.begin(), taps.end(), [&](const Tap& a, const Tap& b) {
             return std::make_tuple(a.group, a.off, kx_of(a), a.out) < std::make_tuple(b.group, b.off, kx_of(b), b.out);

@@ -467,64 +467,101 @@ struct HeadScratch {
 struct HeadParams {
     const float *g2, *b2, *g3, *b3, *w1, *bias1, *w2, *bias2;   // bn2, bn3, linear1 (32,48), linear2 (1,32)
 };
+// AvgPool2d(4): rows 4g..4g+3, cols 0..3; feature f = c * 3 + g   (models.py:229-230).  Grid over (sample, feature).
 __global__ void __launch_bounds__(256)
-head_fwd_kernel(TPlane y, int B, HeadParams hp, const float* __restrict__ mask1, const float* __restrict__ mask2, float keep_scale,
+head_pool_kernel(TPlane y, int B, float* __restrict__ pooled) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * kHeadFeat) return;
+    const int b = i / kHeadFeat, f = i % kHeadFeat, c = f / 3, g = f % 3;
+    float a = 0.f;
+    for (int r = 4 * g; r < 4 * g + 4; ++r)
+        for (int col = 0; col < 4; ++col) {
+            int which;
+            const long long p = tpix(y, b, r, col, which);
+            a += __bfloat162float(y.base[which][(c / 8) * y.kc_stride + p * 8 + (c % 8)]);
+        }
+    pooled[i] = a * (1.f / 16.f);
+}
+// Average-pool backward into the (plain) gradient plane of the last block output: every real pixel is written (zeros outside
+// the pooled 12 x 4 corner).  Grid over (sample, pixel, 8-channel chunk), one 16-byte store each.
+__global__ void __launch_bounds__(256)
+head_unpool_kernel(TPlane dy, int B, const float* __restrict__ dpool) {
+    const int chunks = dy.C / 8;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * dy.H * dy.W * chunks) return;
+    const int col = i % dy.W, r = (i / dy.W) % dy.H, kc = (i / (dy.W * dy.H)) % chunks, b = i / (dy.W * dy.H * chunks);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        v[e] = (r < 12 && col < 4) ? dpool[b * kHeadFeat + (kc * 8 + e) * 3 + r / 4] * (1.f / 16.f) : 0.f;
+    int which;
+    const long long p = tpix(dy, b, r, col, which);
+    store8(dy.base[which] + kc * dy.kc_stride + p * 8, v);
+}
+
+// The dense part of the head on (B, 48) / (B, 32) matrices, one CTA.  Batch reductions: warp w owns features w, w + n_warps, ...,
+// its lanes stride over the samples and combine with shuffles; everything element-wise runs over all threads.
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__global__ void __launch_bounds__(1024)
+head_fwd_kernel(int B, HeadParams hp, const float* __restrict__ mask1, const float* __restrict__ mask2, float keep_scale,
                 HeadScratch s, float* __restrict__ probs, float* __restrict__ stat_out /* mean2 var2 mean3 var3 */) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    // AvgPool2d(4): rows 4g..4g+3, cols 0..3; feature f = c * 3 + g   (models.py:229-230)
-    for (int i = tid; i < B * kHeadFeat; i += nt) {
-        const int b = i / kHeadFeat, f = i % kHeadFeat, c = f / 3, g = f % 3;
-        float a = 0.f;
-        for (int r = 4 * g; r < 4 * g + 4; ++r)
-            for (int col = 0; col < 4; ++col) {
-                int which;
-                const long long p = tpix(y, b, r, col, which);
-                a += __bfloat162float(y.base[which][(c / 8) * y.kc_stride + p * 8 + (c % 8)]);
-            }
-        s.pooled[i] = a * (1.f / 16.f);
-    }
-    __syncthreads();
-    // bn2 over the batch (biased variance), dropout 1
-    for (int f = tid; f < kHeadFeat; f += nt) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = nt >> 5;
+    __shared__ float s_mean[kHeadFeat], s_inv[kHeadFeat];
+    // bn2 over the batch (biased variance)
+    for (int f = warp; f < kHeadFeat; f += n_warps) {
         float m = 0.f, q = 0.f;
-        for (int b = 0; b < B; ++b) m += s.pooled[b * kHeadFeat + f];
-        m /= B;
-        for (int b = 0; b < B; ++b) { const float d = s.pooled[b * kHeadFeat + f] - m; q += d * d; }
-        q /= B;
-        const float inv = rsqrtf(q + kBnEps);
-        s.inv2[f] = inv;
-        stat_out[f] = m; stat_out[kHeadFeat + f] = q;
-        for (int b = 0; b < B; ++b) {
-            const float xh = (s.pooled[b * kHeadFeat + f] - m) * inv;
-            s.xh2[b * kHeadFeat + f] = xh;
-            s.d1[b * kHeadFeat + f] = fmaf(xh, hp.g2[f], hp.b2[f]) * mask1[b * kHeadFeat + f] * keep_scale;
+        for (int b = lane; b < B; b += 32) m += s.pooled[b * kHeadFeat + f];
+        m = warp_sum(m) / B;
+        for (int b = lane; b < B; b += 32) { const float d = s.pooled[b * kHeadFeat + f] - m; q += d * d; }
+        q = warp_sum(q) / B;
+        if (lane == 0) {
+            const float inv = rsqrtf(q + kBnEps);
+            s_mean[f] = m; s_inv[f] = inv;
+            s.inv2[f] = inv;
+            stat_out[f] = m; stat_out[kHeadFeat + f] = q;
         }
     }
     __syncthreads();
-    for (int i = tid; i < B * kHeadHidden; i += nt) {
+    for (int i = tid; i < B * kHeadFeat; i += nt) {   // normalise, affine, dropout 1
+        const int f = i % kHeadFeat;
+        const float xh = (s.pooled[i] - s_mean[f]) * s_inv[f];
+        s.xh2[i] = xh;
+        s.d1[i] = fmaf(xh, hp.g2[f], hp.b2[f]) * mask1[i] * keep_scale;
+    }
+    __syncthreads();
+    for (int i = tid; i < B * kHeadHidden; i += nt) {   // linear1
         const int b = i / kHeadHidden, o = i % kHeadHidden;
         float a = hp.bias1[o];
         for (int f = 0; f < kHeadFeat; ++f) a = fmaf(hp.w1[o * kHeadFeat + f], s.d1[b * kHeadFeat + f], a);
         s.l1[i] = a;
     }
     __syncthreads();
-    for (int o = tid; o < kHeadHidden; o += nt) {
+    for (int o = warp; o < kHeadHidden; o += n_warps) {   // bn3 over the batch
         float m = 0.f, q = 0.f;
-        for (int b = 0; b < B; ++b) m += s.l1[b * kHeadHidden + o];
-        m /= B;
-        for (int b = 0; b < B; ++b) { const float d = s.l1[b * kHeadHidden + o] - m; q += d * d; }
-        q /= B;
-        const float inv = rsqrtf(q + kBnEps);
-        s.inv3[o] = inv;
-        stat_out[2 * kHeadFeat + o] = m; stat_out[2 * kHeadFeat + kHeadHidden + o] = q;
-        for (int b = 0; b < B; ++b) {
-            const float xh = (s.l1[b * kHeadHidden + o] - m) * inv;
-            s.xh3[b * kHeadHidden + o] = xh;
-            s.d2[b * kHeadHidden + o] = fmaf(xh, hp.g3[o], hp.b3[o]) * mask2[b * kHeadHidden + o] * keep_scale;
+        for (int b = lane; b < B; b += 32) m += s.l1[b * kHeadHidden + o];
+        m = warp_sum(m) / B;
+        for (int b = lane; b < B; b += 32) { const float d = s.l1[b * kHeadHidden + o] - m; q += d * d; }
+        q = warp_sum(q) / B;
+        if (lane == 0) {
+            const float inv = rsqrtf(q + kBnEps);
+            s_mean[o] = m; s_inv[o] = inv;
+            s.inv3[o] = inv;
+            stat_out[2 * kHeadFeat + o] = m; stat_out[2 * kHeadFeat + kHeadHidden + o] = q;
         }
     }
     __syncthreads();
-    for (int b = tid; b < B; b += nt) {
+    for (int i = tid; i < B * kHeadHidden; i += nt) {   // normalise, affine, dropout 2 (the ReLU is applied by the consumers)
+        const int o = i % kHeadHidden;
+        const float xh = (s.l1[i] - s_mean[o]) * s_inv[o];
+        s.xh3[i] = xh;
+        s.d2[i] = fmaf(xh, hp.g3[o], hp.b3[o]) * mask2[i] * keep_scale;
+    }
+    __syncthreads();
+    for (int b = tid; b < B; b += nt) {   // linear2 + sigmoid
         float zacc = hp.bias2[0];
         for (int o = 0; o < kHeadHidden; ++o) zacc = fmaf(hp.w2[o], fmaxf(s.d2[b * kHeadHidden + o], 0.f), zacc);
         const float p = 1.f / (1.f + expf(-zacc));
@@ -537,46 +574,54 @@ struct HeadGrads {
     float *g2, *b2, *g3, *b3, *w1, *bias1, *w2, *bias2;
 };
 // Scratch for backward (floats): dl1[B][32] dd1[B][48] dpool[B][48]
-__global__ void __launch_bounds__(256)
-head_bwd_kernel(TPlane dy, int B, HeadParams hp, const float* __restrict__ mask1, const float* __restrict__ mask2, float keep_scale,
+__global__ void __launch_bounds__(1024)
+head_bwd_kernel(int B, HeadParams hp, const float* __restrict__ mask1, const float* __restrict__ mask2, float keep_scale,
                 HeadScratch s, const float* __restrict__ dprobs, float* __restrict__ dl1, float* __restrict__ dd1,
                 float* __restrict__ dpool, HeadGrads hg) {
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = nt >> 5;
     __shared__ float s_dz[1024];   // dL/dlogit per sample (B <= 1024)
+    __shared__ float s_sg[kHeadFeat], s_sgx[kHeadFeat];
     for (int b = tid; b < B; b += nt) s_dz[b] = dprobs[b] * s.out[b] * (1.f - s.out[b]);
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
         float a = 0.f;
-        for (int b = 0; b < B; ++b) a += s_dz[b];
-        hg.bias2[0] = a;
+        for (int b = lane; b < B; b += 32) a += s_dz[b];
+        a = warp_sum(a);
+        if (lane == 0) hg.bias2[0] = a;
     }
-    // linear2, relu, dropout 2, bn3
-    for (int o = tid; o < kHeadHidden; o += nt) {
+    // linear2, relu, dropout 2: da3 = dL/d(bn3 output); reductions for dW2, dgamma3, dbeta3
+    for (int o = warp; o < kHeadHidden; o += n_warps) {
         float dw2 = 0.f, sg = 0.f, sgx = 0.f;
-        for (int b = 0; b < B; ++b) {
+        for (int b = lane; b < B; b += 32) {
             const float d2 = s.d2[b * kHeadHidden + o];
             dw2 = fmaf(s_dz[b], fmaxf(d2, 0.f), dw2);
             const float da3 = (d2 > 0.f ? s_dz[b] * hp.w2[o] : 0.f) * mask2[b * kHeadHidden + o] * keep_scale;
             sg += da3;
             sgx = fmaf(da3, s.xh3[b * kHeadHidden + o], sgx);
         }
-        hg.w2[o] = dw2; hg.g3[o] = sgx; hg.b3[o] = sg;
-        float db1 = 0.f;
-        for (int b = 0; b < B; ++b) {
-            const float d2 = s.d2[b * kHeadHidden + o];
-            const float da3 = (d2 > 0.f ? s_dz[b] * hp.w2[o] : 0.f) * mask2[b * kHeadHidden + o] * keep_scale;
-            const float v = hp.g3[o] * s.inv3[o] * (da3 - sg / B - s.xh3[b * kHeadHidden + o] * sgx / B);
-            dl1[b * kHeadHidden + o] = v;
-            db1 += v;
-        }
-        hg.bias1[o] = db1;
+        dw2 = warp_sum(dw2); sg = warp_sum(sg); sgx = warp_sum(sgx);
+        if (lane == 0) { hg.w2[o] = dw2; hg.g3[o] = sgx; hg.b3[o] = sg; s_sg[o] = sg; s_sgx[o] = sgx; }
     }
     __syncthreads();
-    for (int i = tid; i < kHeadHidden * kHeadFeat; i += nt) {   // dW1[o][f] = sum_b dl1[b][o] d1[b][f]
+    for (int i = tid; i < B * kHeadHidden; i += nt) {   // bn3 backward
+        const int b = i / kHeadHidden, o = i % kHeadHidden;
+        const float d2 = s.d2[i];
+        const float da3 = (d2 > 0.f ? s_dz[b] * hp.w2[o] : 0.f) * mask2[i] * keep_scale;
+        dl1[i] = hp.g3[o] * s.inv3[o] * (da3 - s_sg[o] / B - s.xh3[i] * s_sgx[o] / B);
+    }
+    __syncthreads();
+    for (int o = warp; o < kHeadHidden; o += n_warps) {   // dbias1
+        float a = 0.f;
+        for (int b = lane; b < B; b += 32) a += dl1[b * kHeadHidden + o];
+        a = warp_sum(a);
+        if (lane == 0) hg.bias1[o] = a;
+    }
+    for (int i = warp; i < kHeadHidden * kHeadFeat; i += n_warps) {   // dW1[o][f] = sum_b dl1[b][o] d1[b][f]
         const int o = i / kHeadFeat, f = i % kHeadFeat;
         float a = 0.f;
-        for (int b = 0; b < B; ++b) a = fmaf(dl1[b * kHeadHidden + o], s.d1[b * kHeadFeat + f], a);
-        hg.w1[i] = a;
+        for (int b = lane; b < B; b += 32) a = fmaf(dl1[b * kHeadHidden + o], s.d1[b * kHeadFeat + f], a);
+        a = warp_sum(a);
+        if (lane == 0) hg.w1[i] = a;
     }
     for (int i = tid; i < B * kHeadFeat; i += nt) {   // dd1 = W1^T dl1, through dropout 1
         const int b = i / kHeadFeat, f = i % kHeadFeat;
@@ -585,23 +630,16 @@ head_bwd_kernel(TPlane dy, int B, HeadParams hp, const float* __restrict__ mask1
         dd1[i] = a * mask1[i] * keep_scale;
     }
     __syncthreads();
-    for (int f = tid; f < kHeadFeat; f += nt) {   // bn2 backward
+    for (int f = warp; f < kHeadFeat; f += n_warps) {   // bn2 backward: reductions
         float sg = 0.f, sgx = 0.f;
-        for (int b = 0; b < B; ++b) { sg += dd1[b * kHeadFeat + f]; sgx = fmaf(dd1[b * kHeadFeat + f], s.xh2[b * kHeadFeat + f], sgx); }
-        hg.g2[f] = sgx; hg.b2[f] = sg;
-        for (int b = 0; b < B; ++b)
-            dpool[b * kHeadFeat + f] = hp.g2[f] * s.inv2[f] * (dd1[b * kHeadFeat + f] - sg / B - s.xh2[b * kHeadFeat + f] * sgx / B);
+        for (int b = lane; b < B; b += 32) { sg += dd1[b * kHeadFeat + f]; sgx = fmaf(dd1[b * kHeadFeat + f], s.xh2[b * kHeadFeat + f], sgx); }
+        sg = warp_sum(sg); sgx = warp_sum(sgx);
+        if (lane == 0) { hg.g2[f] = sgx; hg.b2[f] = sg; s_sg[f] = sg; s_sgx[f] = sgx; }
     }
     __syncthreads();
-    // average-pool backward into the (plain) gradient plane of the last block output; untouched elements stay zero
-    const int C = dy.C;
-    for (int i = tid; i < B * C * dy.H * dy.W; i += nt) {
-        const int col = i % dy.W, r = (i / dy.W) % dy.H, c = (i / (dy.W * dy.H)) % C, b = i / (dy.W * dy.H * C);
-        float v = 0.f;
-        if (r < 12 && col < 4) v = dpool[b * kHeadFeat + c * 3 + r / 4] * (1.f / 16.f);
-        int which;
-        const long long p = tpix(dy, b, r, col, which);
-        dy.base[which][(c / 8) * dy.kc_stride + p * 8 + (c % 8)] = __float2bfloat16_rn(v);
+    for (int i = tid; i < B * kHeadFeat; i += nt) {
+        const int f = i % kHeadFeat;
+        dpool[i] = hp.g2[f] * s.inv2[f] * (dd1[i] - s_sg[f] / B - s.xh2[i] * s_sgx[f] / B);
     }
 }
 
@@ -1177,8 +1215,10 @@ cudaError_t train_forward(TrainNet* n, const float* params, const float* x, int 
     LD_TRY(cudaGetLastError());
     // head (+ its two BatchNorm1d statistics straight into bn_stats)
     const int head_stat0 = n->head_bn2.stat_out;
-    head_fwd_kernel<<<1, 256, 0, stream>>>(n->levels.back(), B, head_params(n, params), mask1, mask2, n->keep_scale, n->hs, probs,
+    head_pool_kernel<<<blocks_for(static_cast<long long>(B) * kHeadFeat, 256), 256, 0, stream>>>(n->levels.back(), B, n->hs.pooled);
+    head_fwd_kernel<<<1, 1024, 0, stream>>>(B, head_params(n, params), mask1, mask2, n->keep_scale, n->hs, probs,
                                            bn_stats + head_stat0);
+    ++n->launches;
     ++n->launches;
     LD_TRY(cudaGetLastError());
     // conv BatchNorm statistics (mean incl. conv bias, biased variance) for the caller's running-statistics update
@@ -1313,8 +1353,11 @@ cudaError_t train_backward(TrainNet* n, const float* dprobs, float* grads, cudaS
     HeadGrads hg;
     hg.g2 = grads + n->head_off[0]; hg.b2 = grads + n->head_off[1]; hg.g3 = grads + n->head_off[2]; hg.b3 = grads + n->head_off[3];
     hg.w1 = grads + n->head_off[4]; hg.bias1 = grads + n->head_off[5]; hg.w2 = grads + n->head_off[6]; hg.bias2 = grads + n->head_off[7];
-    head_bwd_kernel<<<1, 256, 0, stream>>>(n->dy_last, B, head_params(n, params), n->mask1_d, n->mask2_d, n->keep_scale, n->hs, dprobs,
+    head_bwd_kernel<<<1, 1024, 0, stream>>>(B, head_params(n, params), n->mask1_d, n->mask2_d, n->keep_scale, n->hs, dprobs,
                                            n->dl1, n->dd1, n->dpool, hg);
+    head_unpool_kernel<<<blocks_for(static_cast<long long>(B) * n->dy_last.H * n->dy_last.W * (n->dy_last.C / 8), 256), 256, 0, stream>>>(
+        n->dy_last, B, n->dpool);
+    ++n->launches;
     ++n->launches;
     LD_TRY(cudaGetLastError());
 

@@ -64,6 +64,9 @@ struct alignas(16) GemmJob {          // what the producers and the epilogue nee
     int64_t out_kc_stride;
     int64_t pad_;
 };
+// Position of weight row ky inside a stacked block.
+__host__ __device__ inline int w_stack_row(int order, int ky) { return order == 2 ? (ky == 2 ? 0 : ky + 1) : 2 - ky; }
+
 struct GemmJobTaps {   // where a job's tap program sits in GemmParams::taps
     uint16_t tap0, n_taps, n_stages, pad_;
 };
@@ -84,7 +87,8 @@ struct GemmParams {         // the kernel's __grid_constant__ parameter
     int32_t n_stages;
     int32_t groups_per_stage;  // consecutive groups of a job that share one smem stage (one barrier round trip)
     uint32_t wp_magic;  // floor(2^32 / wp) + 1: row = umulhi(pixel, wp_magic)
-    int32_t w_stack;    // 1: 3x3 weights are re-stacked in smem as [kx][cin/8][ky = 2,1,0][cout][8] (slab 9, if any, stays a slab)
+    int32_t w_stack;    // 1, 2: 3x3 weights are re-stacked in smem as [kx][cin/8][ky order][cout][8], order ky = 2,1,0 (1) or
+                        // 2,0,1 (2, stride-2 convs), see w_stack_row; slab 9, if any, stays a slab.  0: plain slabs
     int32_t dbg;        // timing experiments only (LD_GEMM_DBG, results are garbage): bit 0 one copy per smem stage, bit 1 no MMAs,
                         // bit 2 no global stores, bit 3 no TMEM reads/clears in the epilogue
     int32_t n_issuers;  // MMA-issuing warps = accumulator stages (2: 256 columns each, 4: 128 columns each)

@@ -43,7 +43,8 @@ template <int CIN, int COUT>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_mma_kernel(const __grid_constant__ WgradLaunch L) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (warp index through a shuffle: the compiler then keeps the issuing warp's descriptor arithmetic in uniform registers)
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     constexpr int kSegPerMma = 128 / CIN;
     constexpr uint32_t seg_bytes = (CIN / 8) * kWgSegPx * 16u;
     constexpr uint32_t dz_bytes = (COUT / 8) * kWgTile * 16u;

@@ -310,18 +310,8 @@ class Engine:
 
     @property
     def gemm_plane_bytes_per_row(self):
-        """Activation bytes the conv launches move per sequence row if every plane crosses HBM once per launch that touches
-        it: for each launch the distinct input planes, residual planes and output planes (fp16, wp x C per row)."""
-        plan = _native.plan_json(self.cfg)
-        size = {p["id"]: 2 * p["wp"] * p["C"] for p in plan["planes"]}
-        total = 0
-        for c in plan["convs"]:
-            touched = set()
-            for job in c["jobs"]:
-                touched.update(p for p, _, _ in job["taps"])
-                touched.update(x for x in (job["res"], job["out0"], job.get("out1", -1)) if x >= 0)
-            total += sum(size[i] for i in touched)
-        return float(total)
+        """Algorithmic HBM traffic of the conv stack per sequence row (see _native.plan_plane_bytes_per_row)."""
+        return _native.plan_plane_bytes_per_row(self.cfg)
 
     def timing_enable(self, enable=True):
         check(self.lib.ld_timing_enable(self._h, int(bool(enable))))

@@ -92,10 +92,11 @@ def _expand_tap_program(conv):
                     assert n == cout and b16 % (kchunks * cout) == 0
                     wtap = b16 // (kchunks * cout)
                 else:
-                    assert conv["w_stack"] == 1
+                    assert conv["w_stack"] in (1, 2)
                     kx, rem = divmod(b16, kchunks * 3 * cout)
                     assert rem % cout == 0 and rem // cout + n // cout <= 3
-                    wtap = (2 - (rem // cout + i)) * 3 + kx
+                    ky = {1: (2, 1, 0), 2: (2, 0, 1)}[conv["w_stack"]][rem // cout + i]   # stacking order of the weight rows
+                    wtap = ky * 3 + kx
                 products.append((job["outs"][col // cout + i][0], src, gshift + off, wtap))
             if last:
                 n_last += 1; open_stage = False
@@ -122,3 +123,12 @@ def test_tap_program_covers_the_plan():
         merged += len(want) - sum(len(j["taps"]) for j in gc["jobs"])
         assert gc["n_stages"] >= 2 and gc["n_rings"] in (1, 2) and gc["n_issuers"] in (2, 4)
     assert merged > 300, "chains of window-specific rows share their input loads and MMAs"
+
+
+def test_plane_traffic_per_row():
+    """The algorithmic HBM traffic of the conv stack behind bench.py's roofline: ~733 KB of fp16 planes per frame, i.e. 85 FLOP
+    per byte with the 62.4 MMAC the plan executes -- left of the B200 ridge, the stack is HBM-bound."""
+    b = _native.plan_plane_bytes_per_row()
+    assert b == 732928.0
+    plan = _native.plan_json()
+    assert 80 < 2 * plan["macs_per_row"] / b < 180
