@@ -499,31 +499,51 @@ head_unpool_kernel(TPlane dy, int B, const float* __restrict__ dpool) {
     store8(dy.base[which] + kc * dy.kc_stride + p * 8, v);
 }
 
-// The dense part of the head on (B, 48) / (B, 32) matrices, one CTA.  Batch reductions: warp w owns features w, w + n_warps, ...,
-// its lanes stride over the samples and combine with shuffles; everything element-wise runs over all threads.
-__device__ __forceinline__ float warp_sum(float v) {
+// The dense part of the head on (B, 48) / (B, 32) matrices, one CTA of 1024 threads.  Batch reductions per feature: thread t
+// owns feature t % F and the samples t / F, t / F + slices, ... (adjacent threads read adjacent features: coalesced), the
+// slices are combined through shared memory; everything element-wise runs over all threads.
+constexpr int kHeadThreads = 1024;
+template <int NV, typename Fn>
+__device__ __forceinline__ void column_reduce(int B, int F, float (*s_part)[kHeadThreads], float (*s_out)[kHeadFeat], Fn fn) {
+    const int tid = threadIdx.x, slices = kHeadThreads / F, f = tid % F, sl = tid / F;
+    float acc[NV];
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    for (int k = 0; k < NV; ++k) acc[k] = 0.f;
+    if (sl < slices)
+        for (int b = sl; b < B; b += slices) fn(b, f, acc);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s_part[k][tid] = acc[k];
+    __syncthreads();
+    if (tid < F) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            float a = 0.f;
+            for (int j = 0; j < slices; ++j) a += s_part[k][j * F + tid];
+            s_out[k][tid] = a;
+        }
+    }
+    __syncthreads();
 }
-__global__ void __launch_bounds__(1024)
+
+__global__ void __launch_bounds__(kHeadThreads)
 head_fwd_kernel(int B, HeadParams hp, const float* __restrict__ mask1, const float* __restrict__ mask2, float keep_scale,
                 HeadScratch s, float* __restrict__ probs, float* __restrict__ stat_out /* mean2 var2 mean3 var3 */) {
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = nt >> 5;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ float s_part[3][kHeadThreads], s_red[3][kHeadFeat];
     __shared__ float s_mean[kHeadFeat], s_inv[kHeadFeat];
-    // bn2 over the batch (biased variance)
-    for (int f = warp; f < kHeadFeat; f += n_warps) {
-        float m = 0.f, q = 0.f;
-        for (int b = lane; b < B; b += 32) m += s.pooled[b * kHeadFeat + f];
-        m = warp_sum(m) / B;
-        for (int b = lane; b < B; b += 32) { const float d = s.pooled[b * kHeadFeat + f] - m; q += d * d; }
-        q = warp_sum(q) / B;
-        if (lane == 0) {
-            const float inv = rsqrtf(q + kBnEps);
-            s_mean[f] = m; s_inv[f] = inv;
-            s.inv2[f] = inv;
-            stat_out[f] = m; stat_out[kHeadFeat + f] = q;
-        }
+    // bn2 over the batch (biased variance, two passes)
+    column_reduce<1>(B, kHeadFeat, s_part, s_red, [&](int b, int f, float* a) { a[0] += s.pooled[b * kHeadFeat + f]; });
+    if (tid < kHeadFeat) s_mean[tid] = s_red[0][tid] / B;
+    __syncthreads();
+    column_reduce<1>(B, kHeadFeat, s_part, s_red, [&](int b, int f, float* a) {
+        const float d = s.pooled[b * kHeadFeat + f] - s_mean[f];
+        a[0] = fmaf(d, d, a[0]);
+    });
+    if (tid < kHeadFeat) {
+        const float q = s_red[0][tid] / B, inv = rsqrtf(q + kBnEps);
+        s_inv[tid] = inv;
+        s.inv2[tid] = inv;
+        stat_out[tid] = s_mean[tid]; stat_out[kHeadFeat + tid] = q;
     }
     __syncthreads();
     for (int i = tid; i < B * kHeadFeat; i += nt) {   // normalise, affine, dropout 1
@@ -540,18 +560,19 @@ head_fwd_kernel(int B, HeadParams hp, const float* __restrict__ mask1, const flo
         s.l1[i] = a;
     }
     __syncthreads();
-    for (int o = warp; o < kHeadHidden; o += n_warps) {   // bn3 over the batch
-        float m = 0.f, q = 0.f;
-        for (int b = lane; b < B; b += 32) m += s.l1[b * kHeadHidden + o];
-        m = warp_sum(m) / B;
-        for (int b = lane; b < B; b += 32) { const float d = s.l1[b * kHeadHidden + o] - m; q += d * d; }
-        q = warp_sum(q) / B;
-        if (lane == 0) {
-            const float inv = rsqrtf(q + kBnEps);
-            s_mean[o] = m; s_inv[o] = inv;
-            s.inv3[o] = inv;
-            stat_out[2 * kHeadFeat + o] = m; stat_out[2 * kHeadFeat + kHeadHidden + o] = q;
-        }
+    // bn3 over the batch
+    column_reduce<1>(B, kHeadHidden, s_part, s_red, [&](int b, int o, float* a) { a[0] += s.l1[b * kHeadHidden + o]; });
+    if (tid < kHeadHidden) s_mean[tid] = s_red[0][tid] / B;
+    __syncthreads();
+    column_reduce<1>(B, kHeadHidden, s_part, s_red, [&](int b, int o, float* a) {
+        const float d = s.l1[b * kHeadHidden + o] - s_mean[o];
+        a[0] = fmaf(d, d, a[0]);
+    });
+    if (tid < kHeadHidden) {
+        const float q = s_red[0][tid] / B, inv = rsqrtf(q + kBnEps);
+        s_inv[tid] = inv;
+        s.inv3[tid] = inv;
+        stat_out[2 * kHeadFeat + tid] = s_mean[tid]; stat_out[2 * kHeadFeat + kHeadHidden + tid] = q;
     }
     __syncthreads();
     for (int i = tid; i < B * kHeadHidden; i += nt) {   // normalise, affine, dropout 2 (the ReLU is applied by the consumers)
@@ -574,54 +595,43 @@ struct HeadGrads {
     float *g2, *b2, *g3, *b3, *w1, *bias1, *w2, *bias2;
 };
 // Scratch for backward (floats): dl1[B][32] dd1[B][48] dpool[B][48]
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kHeadThreads)
 head_bwd_kernel(int B, HeadParams hp, const float* __restrict__ mask1, const float* __restrict__ mask2, float keep_scale,
                 HeadScratch s, const float* __restrict__ dprobs, float* __restrict__ dl1, float* __restrict__ dd1,
                 float* __restrict__ dpool, HeadGrads hg) {
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = nt >> 5;
+    const int tid = threadIdx.x, nt = blockDim.x;
     __shared__ float s_dz[1024];   // dL/dlogit per sample (B <= 1024)
-    __shared__ float s_sg[kHeadFeat], s_sgx[kHeadFeat];
+    __shared__ float s_part[3][kHeadThreads], s_red[3][kHeadFeat];
     for (int b = tid; b < B; b += nt) s_dz[b] = dprobs[b] * s.out[b] * (1.f - s.out[b]);
     __syncthreads();
-    if (warp == 0) {
-        float a = 0.f;
-        for (int b = lane; b < B; b += 32) a += s_dz[b];
-        a = warp_sum(a);
-        if (lane == 0) hg.bias2[0] = a;
-    }
-    // linear2, relu, dropout 2: da3 = dL/d(bn3 output); reductions for dW2, dgamma3, dbeta3
-    for (int o = warp; o < kHeadHidden; o += n_warps) {
-        float dw2 = 0.f, sg = 0.f, sgx = 0.f;
-        for (int b = lane; b < B; b += 32) {
-            const float d2 = s.d2[b * kHeadHidden + o];
-            dw2 = fmaf(s_dz[b], fmaxf(d2, 0.f), dw2);
-            const float da3 = (d2 > 0.f ? s_dz[b] * hp.w2[o] : 0.f) * mask2[b * kHeadHidden + o] * keep_scale;
-            sg += da3;
-            sgx = fmaf(da3, s.xh3[b * kHeadHidden + o], sgx);
-        }
-        dw2 = warp_sum(dw2); sg = warp_sum(sg); sgx = warp_sum(sgx);
-        if (lane == 0) { hg.w2[o] = dw2; hg.g3[o] = sgx; hg.b3[o] = sg; s_sg[o] = sg; s_sgx[o] = sgx; }
-    }
-    __syncthreads();
+    // linear2, relu, dropout 2: da3 = dL/d(bn3 output); reductions for dW2, dbeta3, dgamma3 (and dbias2 = sum of dz)
+    column_reduce<3>(B, kHeadHidden, s_part, s_red, [&](int b, int o, float* a) {
+        const float d2 = s.d2[b * kHeadHidden + o];
+        a[0] = fmaf(s_dz[b], fmaxf(d2, 0.f), a[0]);
+        const float da3 = (d2 > 0.f ? s_dz[b] * hp.w2[o] : 0.f) * mask2[b * kHeadHidden + o] * keep_scale;
+        a[1] += da3;
+        a[2] = fmaf(da3, s.xh3[b * kHeadHidden + o], a[2]);
+    });
+    if (tid < kHeadHidden) { hg.w2[tid] = s_red[0][tid]; hg.b3[tid] = s_red[1][tid]; hg.g3[tid] = s_red[2][tid]; }
     for (int i = tid; i < B * kHeadHidden; i += nt) {   // bn3 backward
         const int b = i / kHeadHidden, o = i % kHeadHidden;
         const float d2 = s.d2[i];
         const float da3 = (d2 > 0.f ? s_dz[b] * hp.w2[o] : 0.f) * mask2[i] * keep_scale;
-        dl1[i] = hp.g3[o] * s.inv3[o] * (da3 - s_sg[o] / B - s.xh3[i] * s_sgx[o] / B);
+        dl1[i] = hp.g3[o] * s.inv3[o] * (da3 - s_red[1][o] / B - s.xh3[i] * s_red[2][o] / B);
     }
     __syncthreads();
-    for (int o = warp; o < kHeadHidden; o += n_warps) {   // dbias1
-        float a = 0.f;
-        for (int b = lane; b < B; b += 32) a += dl1[b * kHeadHidden + o];
-        a = warp_sum(a);
-        if (lane == 0) hg.bias1[o] = a;
-    }
-    for (int i = warp; i < kHeadHidden * kHeadFeat; i += n_warps) {   // dW1[o][f] = sum_b dl1[b][o] d1[b][f]
+    // dbias1 = column sums of dl1; dbias2 = sum of dz (column 0 of a one-column reduction)
+    column_reduce<1>(B, kHeadHidden, s_part, s_red, [&](int b, int o, float* a) { a[0] += dl1[b * kHeadHidden + o]; });
+    if (tid < kHeadHidden) hg.bias1[tid] = s_red[0][tid];
+    __syncthreads();
+    column_reduce<1>(B, 1, s_part, s_red, [&](int b, int, float* a) { a[0] += s_dz[b]; });
+    if (tid == 0) hg.bias2[0] = s_red[0][0];
+    for (int i = tid; i < kHeadHidden * kHeadFeat; i += nt) {   // dW1[o][f] = sum_b dl1[b][o] d1[b][f]; adjacent threads: adjacent f
         const int o = i / kHeadFeat, f = i % kHeadFeat;
         float a = 0.f;
-        for (int b = lane; b < B; b += 32) a = fmaf(dl1[b * kHeadHidden + o], s.d1[b * kHeadFeat + f], a);
-        a = warp_sum(a);
-        if (lane == 0) hg.w1[i] = a;
+#pragma unroll 8
+        for (int b = 0; b < B; ++b) a = fmaf(dl1[b * kHeadHidden + o], s.d1[b * kHeadFeat + f], a);
+        hg.w1[i] = a;
     }
     for (int i = tid; i < B * kHeadFeat; i += nt) {   // dd1 = W1^T dl1, through dropout 1
         const int b = i / kHeadFeat, f = i % kHeadFeat;
@@ -630,16 +640,15 @@ head_bwd_kernel(int B, HeadParams hp, const float* __restrict__ mask1, const flo
         dd1[i] = a * mask1[i] * keep_scale;
     }
     __syncthreads();
-    for (int f = warp; f < kHeadFeat; f += n_warps) {   // bn2 backward: reductions
-        float sg = 0.f, sgx = 0.f;
-        for (int b = lane; b < B; b += 32) { sg += dd1[b * kHeadFeat + f]; sgx = fmaf(dd1[b * kHeadFeat + f], s.xh2[b * kHeadFeat + f], sgx); }
-        sg = warp_sum(sg); sgx = warp_sum(sgx);
-        if (lane == 0) { hg.g2[f] = sgx; hg.b2[f] = sg; s_sg[f] = sg; s_sgx[f] = sgx; }
-    }
-    __syncthreads();
+    // bn2 backward
+    column_reduce<2>(B, kHeadFeat, s_part, s_red, [&](int b, int f, float* a) {
+        a[0] += dd1[b * kHeadFeat + f];
+        a[1] = fmaf(dd1[b * kHeadFeat + f], s.xh2[b * kHeadFeat + f], a[1]);
+    });
+    if (tid < kHeadFeat) { hg.b2[tid] = s_red[0][tid]; hg.g2[tid] = s_red[1][tid]; }
     for (int i = tid; i < B * kHeadFeat; i += nt) {
         const int f = i % kHeadFeat;
-        dpool[i] = hp.g2[f] * s.inv2[f] * (dd1[i] - s_sg[f] / B - s.xh2[i] * s_sgx[f] / B);
+        dpool[i] = hp.g2[f] * s.inv2[f] * (dd1[i] - s_red[0][f] / B - s.xh2[i] * s_red[1][f] / B);
     }
 }
 
@@ -1216,7 +1225,7 @@ cudaError_t train_forward(TrainNet* n, const float* params, const float* x, int 
     // head (+ its two BatchNorm1d statistics straight into bn_stats)
     const int head_stat0 = n->head_bn2.stat_out;
     head_pool_kernel<<<blocks_for(static_cast<long long>(B) * kHeadFeat, 256), 256, 0, stream>>>(n->levels.back(), B, n->hs.pooled);
-    head_fwd_kernel<<<1, 1024, 0, stream>>>(B, head_params(n, params), mask1, mask2, n->keep_scale, n->hs, probs,
+    head_fwd_kernel<<<1, kHeadThreads, 0, stream>>>(B, head_params(n, params), mask1, mask2, n->keep_scale, n->hs, probs,
                                            bn_stats + head_stat0);
     ++n->launches;
     ++n->launches;
@@ -1353,7 +1362,7 @@ cudaError_t train_backward(TrainNet* n, const float* dprobs, float* grads, cudaS
     HeadGrads hg;
     hg.g2 = grads + n->head_off[0]; hg.b2 = grads + n->head_off[1]; hg.g3 = grads + n->head_off[2]; hg.b3 = grads + n->head_off[3];
     hg.w1 = grads + n->head_off[4]; hg.bias1 = grads + n->head_off[5]; hg.w2 = grads + n->head_off[6]; hg.bias2 = grads + n->head_off[7];
-    head_bwd_kernel<<<1, 1024, 0, stream>>>(B, head_params(n, params), n->mask1_d, n->mask2_d, n->keep_scale, n->hs, dprobs,
+    head_bwd_kernel<<<1, kHeadThreads, 0, stream>>>(B, head_params(n, params), n->mask1_d, n->mask2_d, n->keep_scale, n->hs, dprobs,
                                            n->dl1, n->dd1, n->dpool, hg);
     head_unpool_kernel<<<blocks_for(static_cast<long long>(B) * n->dy_last.H * n->dy_last.W * (n->dy_last.C / 8), 256), 256, 0, stream>>>(
         n->dy_last, B, n->dpool);

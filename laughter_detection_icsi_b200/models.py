@@ -172,16 +172,31 @@ class ResNetBigger(nn.Module):
 
     @torch.no_grad()
     def _update_running_stats(self, eng, bn_stats, batch):
-        """nn.BatchNorm's running-statistics update (momentum 0.1, unbiased variance), from the kernel's batch statistics."""
-        modules = dict(self.named_modules())
-        for name, off, C in eng.train_table["batchnorms"]:
-            bn = modules[name]
-            mean, var = bn_stats[off:off + C], bn_stats[off + C:off + 2 * C]
-            n = batch * self._bn_pixels(name) if isinstance(bn, nn.BatchNorm2d) else batch
-            m = bn.momentum if bn.momentum is not None else 0.1
-            bn.running_mean.mul_(1 - m).add_(m * mean)
-            bn.running_var.mul_(1 - m).add_(m * var * (n / max(n - 1, 1)))
-            bn.num_batches_tracked += 1
+        """nn.BatchNorm's running-statistics update (momentum 0.1, unbiased variance), from the kernel's batch statistics.
+        Multi-tensor (foreach) ops: six launches for the 22 BatchNorms instead of ~180."""
+        cache = getattr(self, "_bn_update_cache", None)
+        if cache is None or cache["batch"] != batch or any(bn.running_mean is not t for (bn, _, _), t in zip(cache["entries"], cache["rm"])):
+            # (buffers are replaced, not updated in place, by Module.to()/set_device)
+            modules = dict(self.named_modules())
+            entries = [(modules[name], off, C) for name, off, C in eng.train_table["batchnorms"]]
+            keep, mom, var_scale = [], [], []
+            for (bn, _, _), (name, _, _) in zip(entries, eng.train_table["batchnorms"]):
+                n = batch * self._bn_pixels(name) if isinstance(bn, nn.BatchNorm2d) else batch
+                m = bn.momentum if bn.momentum is not None else 0.1
+                keep.append(1.0 - m)
+                mom.append(m)
+                var_scale.append(m * (n / max(n - 1, 1)))
+            cache = {"batch": batch, "entries": entries, "keep": keep, "mom": mom, "var_scale": var_scale,
+                     "rm": [bn.running_mean for bn, _, _ in entries], "rv": [bn.running_var for bn, _, _ in entries],
+                     "nbt": [bn.num_batches_tracked for bn, _, _ in entries]}
+            self._bn_update_cache = cache
+        means = [bn_stats[off:off + C] for _, off, C in cache["entries"]]
+        variances = [bn_stats[off + C:off + 2 * C] for _, off, C in cache["entries"]]
+        torch._foreach_mul_(cache["rm"], cache["keep"])
+        torch._foreach_add_(cache["rm"], torch._foreach_mul(means, cache["mom"]))
+        torch._foreach_mul_(cache["rv"], cache["keep"])
+        torch._foreach_add_(cache["rv"], torch._foreach_mul(variances, cache["var_scale"]))
+        torch._foreach_add_(cache["nbt"], 1)
 
     def _bn_pixels(self, name):
         """Spatial positions per sample seen by a BatchNorm2d of the 100 x 44 input."""
