@@ -65,22 +65,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
         : "memory");
 }
 
-// TMA tiled copy of one 3-D box (global -> smem) described by a CUtensorMap that lives in global memory.
-__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-        : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
 
-// L2 prefetch of a contiguous global range (no shared-memory destination, no completion tracking).
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -105,16 +94,6 @@ __device__ __forceinline__ void tmem_wait_ld() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands, fp32 accumulate, single CTA.
-__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                            uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 // Predicated forms for a warp that runs the issue loop in uniform control flow: only the elected lane issues.
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -145,12 +124,6 @@ __device__ __forceinline__ void umma_commit_pred(uint32_t bar, bool issue) {
         : "memory");
 }
 
-// All previously issued MMAs of this thread arrive on the mbarrier when they complete
-// (implies tcgen05.fence::before_thread_sync).
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
-}
 
 // TMEM -> registers: 32 lanes x 32-bit, 8 consecutive columns per thread.
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
@@ -226,14 +199,6 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[N]) {
     if (N - n32 - n16) tmem_ld8(taddr + n32 + n16, v + n32 + n16);
 }
 
-// 16-byte read-only global load that does not allocate in L1 (streamed once per tile).
-__device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p));
-    return v;
-}
 
 // ---------------------------------------------------------------- descriptors
 __device__ __forceinline__ uint64_t umma_pack_desc(uint32_t lo, uint32_t hi) {
