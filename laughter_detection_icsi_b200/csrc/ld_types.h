@@ -21,7 +21,7 @@ namespace ld {
 constexpr int kTileM = 128;      // output pixels per MMA tile (UMMA M)
 constexpr int kMaxGroups = 16;   // distinct smem loads per job
 constexpr int kMaxTaps = 32;     // MMA taps per job
-constexpr int kMaxLaunchTaps = 128;  // MMA taps per launch (all jobs)
+constexpr int kMaxLaunchTaps = 192;  // MMA taps per launch (all jobs; 16 unmerged 3x3 outputs + residuals = 160)
 constexpr int kMaxOuts = 8;      // output planes per job (their accumulators sit side by side in TMEM)
 constexpr int kTmemCols = 512;   // accumulator columns per SM, split into n_issuers stages: n_outs * cout <= 512 / n_issuers
 constexpr int kMaxJobs = 16;     // jobs per launch (the planner also splits a layer into launches of at most this many output planes)
