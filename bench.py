@@ -165,7 +165,7 @@ def time_training(local_rank, world, batch, steps, warmup):
 # ----------------------------------------------------------------------------------------------------- GPU arm
 def run_b200(args):
     import torch.distributed as dist
-    from laughter_detection_icsi_b200 import synth
+    from laughter_detection_icsi_b200 import _native, synth
     from laughter_detection_icsi_b200.pipeline import LaughterPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -293,6 +293,8 @@ def run_b200(args):
                 "class_ms_per_step": {name: round(v[0] / args.steps, 3) for name, v in timing.items()},
                 "peak_source": peaks["source"], "traffic": prof.get("gemm_dram_bytes_per_launch"),
                 "traffic_note": "DRAM read+write bytes of the block1.1.conv2 launch (largest conv launch, 32768 window starts) from ncu --set full, profiles/",
+                "traffic_algorithmic": _native.plan_plane_bytes_per_row(eng.cfg, conv="block1.1.conv2") * (32768 + 100),
+                "traffic_algorithmic_note": "plane bytes of that same launch (32768 window starts + 100 halo rows)",
                 "fbank": {"bound": "hbm", "unit": "GB/s", "achieved": 496.0 * windows_per_step * args.steps / (fbank_ms * 1e-3) / 1e9
                           if fbank_ms else None, "peak": peaks["hbm_gbs"], "ms_per_step": fbank_ms / args.steps,
                           "note": "K1 is fp32-ALU bound (exact 512-point FFT), see DESIGN.md"},

@@ -127,14 +127,17 @@ def plan_json(cfg=None):
     return json.loads(buf.value.decode())
 
 
-def plan_plane_bytes_per_row(cfg=None):
+def plan_plane_bytes_per_row(cfg=None, conv=None):
     """Activation bytes the conv launches of the streaming plan move per sequence row if every plane crosses HBM once per
     launch that touches it: for each launch its distinct input, residual and output planes (fp16, wp x C per row).  This is
-    the algorithmic traffic figure behind bench.py's HBM roofline."""
+    the algorithmic traffic figure behind bench.py's HBM roofline.  `conv` restricts the sum to the
+    launches of one conv layer (e.g. "block1.1.conv2")."""
     plan = plan_json(cfg)
     size = {p["id"]: 2 * p["wp"] * p["C"] for p in plan["planes"]}
     total = 0
     for c in plan["convs"]:
+        if conv is not None and c["conv"] != conv:
+            continue
         touched = set()
         for job in c["jobs"]:
             touched.update(p for p, _, _ in job["taps"])
