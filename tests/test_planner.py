@@ -2,6 +2,7 @@
 evaluation of every window -- validates row classification, tap shifts, even/odd column planes, residual
 routing and the head's row order without a GPU."""
 import numpy as np
+import pytest
 import torch
 
 from laughter_detection_icsi_b200 import _native
@@ -105,10 +106,13 @@ def _expand_tap_program(conv):
     return products
 
 
-def test_tap_program_covers_the_plan():
-    """The N-stacked tap programs (chains of outputs, merged MMAs) multiply exactly the products the plan lists."""
-    plan = _native.plan_json()
-    prog = _native.gemm_program_json()
+@pytest.mark.parametrize("filters", [(64, 32, 16, 16), (64, 48, 32, 16), (64, 64, 32, 16), (64, 16, 16, 16)])
+def test_tap_program_covers_the_plan(filters):
+    """The N-stacked tap programs (chains of outputs, merged MMAs) multiply exactly the products the plan lists -- for
+    resnet_base and for other channel widths the kernels are instantiated for."""
+    cfg = _native.default_config(filter_sizes=filters)
+    plan = _native.plan_json(cfg)
+    prog = _native.gemm_program_json(cfg)
     assert [c["conv"] for c in prog["convs"]] == [c["conv"] for c in plan["convs"]]
     merged = 0
     for pc, gc in zip(plan["convs"], prog["convs"]):
