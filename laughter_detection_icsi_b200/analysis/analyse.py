@@ -161,3 +161,37 @@ def calc_sum_stats(eval_df):
     sum_vals.loc[sum_vals.tot_pred_time == 0, 'precision'] = 1
     sum_vals['recall'] = sum_vals['corr_pred_time'] / sum_vals['tot_transc_laugh_time']
     return sum_vals[['threshold', 'min_len', 'precision', 'recall']]
+
+
+# ------------------------------------------------------------------------------------------------ command line
+def main(argv=None):
+    """python -m laughter_detection_icsi_b200.analysis.analyse --textgrid_dir OUT --segments_csv SEG.csv --info_csv INFO.csv
+
+    OUT is the tree segment_laughter.py writes (<meeting>/t_<thr>/l_<min_len>/chanN.TextGrid); SEG.csv holds the transcribed
+    segments (columns meeting_id, part_id, chan, start, end, length, type in {invalid, laugh, speech, noise}, laugh_type), INFO.csv
+    one row per recorded participant channel (meeting_id, part_id, chan, length).  Writes the per-meeting evaluation dataframe and
+    the corpus summary (config.ANALYSIS file names) into --out_dir, like analyse.py's __main__ does before plotting."""
+    import argparse
+
+    from ..config import ANALYSIS as cfg
+    from . import preprocess
+
+    ap = argparse.ArgumentParser(description=main.__doc__.split("\n")[0])
+    ap.add_argument("--textgrid_dir", required=True)
+    ap.add_argument("--segments_csv", required=True)
+    ap.add_argument("--info_csv", required=True)
+    ap.add_argument("--out_dir", default=".")
+    args = ap.parse_args(argv)
+    seg = pd.read_csv(args.segments_csv)
+    info = pd.read_csv(args.info_csv)
+    by_type = {t: seg[seg["type"] == t] for t in ("invalid", "laugh", "speech", "noise")}
+    indices = preprocess.build_indices(by_type["invalid"], by_type["laugh"], by_type["speech"], by_type["noise"], info)
+    eval_df = create_evaluation_df(args.textgrid_dir, os.path.join(args.out_dir, cfg["eval_df_cache_file"]), indices)
+    stats = calc_sum_stats(eval_df)
+    stats.to_csv(os.path.join(args.out_dir, cfg["sum_stats_cache_file"]), index=False)
+    print(stats.to_string(index=False))
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

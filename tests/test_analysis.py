@@ -167,6 +167,15 @@ def test_textgrid_tree_end_to_end(tmp_path):
             assert (math.isnan(g) and math.isnan(w)) or g == pytest.approx(w, abs=1e-9)
     stats = analyse.calc_sum_stats(df)
     assert list(stats.columns) == ['threshold', 'min_len', 'precision', 'recall'] and len(stats) == 4
+    # the command line does the same from CSV files
+    seg_csv, info_csv, out_dir = tmp_path.parent / "seg.csv", tmp_path.parent / "info.csv", tmp_path.parent / (tmp_path.name + "_cli")
+    pd.concat([pd.DataFrame(v, columns=SEG_COLS) for v in rows.values()]).to_csv(seg_csv, index=False)
+    pd.DataFrame(info).to_csv(info_csv, index=False)
+    os.makedirs(out_dir)
+    assert analyse.main(["--textgrid_dir", str(tmp_path), "--segments_csv", str(seg_csv), "--info_csv", str(info_csv),
+                         "--out_dir", str(out_dir)]) == 0
+    cli_stats = pd.read_csv(out_dir / "sum_stats.csv")
+    assert np.allclose(cli_stats[["precision", "recall"]].to_numpy(), stats[["precision", "recall"]].to_numpy(), equal_nan=True)
     for _, srow in stats.iterrows():
         sel = df[(df.threshold == srow.threshold) & (df.min_len == srow.min_len)]
         tot = sel.tot_pred_time.sum()
