@@ -48,7 +48,11 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
 // The caller presets L's header (weights, shift, cin, cout, n_wtaps, w_stack, relu, wp, out_mode, wp2, hp, mode, stats, prof).
 bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, std::string& err) {
     if (outs.empty()) { err = "no outputs"; return false; }
-    { const char* v = std::getenv("LD_GEMM_DBG"); L.dbg = v ? std::atoi(v) : 0; }
+    {   // knock-out timing experiments produce garbage results: honoured only together with the profiling switch
+        const char* v = std::getenv("LD_GEMM_DBG");
+        const char* p = std::getenv("LD_GEMM_PROF");
+        L.dbg = (v && p && std::atoi(p)) ? std::atoi(v) : 0;
+    }
     if (L.w_stack && L.n_wtaps < 9) { err = "stacked weights need a 3x3 kernel"; return false; }
     // cout >= 48: two issuers with 256 accumulator columns each (chains of up to 4 outputs); narrower layers are bound by
     // the issue latency of their small MMAs: four issuers with 128 columns each
