@@ -45,6 +45,13 @@ enum ld_fbank_preproc {
     LD_PREPROC_FRAME = 1      /* Kaldi / torchaudio.compliance.kaldi: per 400-sample frame */
 };
 
+/* Arithmetic of the conv stack. */
+enum ld_precision {
+    LD_PRECISION_FP16 = 0,  /* fp16 operands, fp32 accumulation everywhere (default; 1e-5 on random-init weights) */
+    LD_PRECISION_SPLIT = 1  /* blocks 2-4 carry weights AND stored activations as hi + lo fp16 pairs (three MMAs per tap):
+                               <= 2e-3 on the calibrated-head checkpoint whose 218x head gain amplifies fp16 rounding */
+};
+
 typedef struct ld_config {
     int32_t struct_size;     /* sizeof(ld_config), for forward compatibility */
     int32_t num_frames;      /* window length in frames, config.FEAT['num_samples'] (config.py:29) = 100 */
@@ -53,7 +60,8 @@ typedef struct ld_config {
     int32_t linear_layer_size; /* config.py:13 = 48 */
     int32_t chunk_rows;      /* window starts evaluated per pass of the conv stack (0 = default 32768) */
     int32_t fbank_preproc;   /* enum ld_fbank_preproc */
-    int32_t reserved[6];
+    int32_t precision;       /* enum ld_precision */
+    int32_t reserved[5];
 } ld_config;
 
 /* One named tensor of a checkpoint's state_dict (host memory, fp32, C-contiguous). */
@@ -82,6 +90,10 @@ LD_API void ld_destroy(ld_ctx* ctx);
 LD_API int ld_fbank_i16(ld_ctx* ctx, const int16_t* pcm_d, const int64_t* chan_len, int32_t n_chan,
                  const float* mel_d, float* feats_d, int64_t* frames_out, void* stream);
 LD_API int64_t ld_fbank_num_frames(int64_t num_samples);
+/* The filterbank behind mel_d is packed into its sparse kernel form when mel_d differs from the previous call's pointer
+ * (one D2H copy + stream synchronisation, then none in the steady state).  A caller that rewrites the matrix IN PLACE must
+ * call this before the next ld_fbank_i16 so that the new contents are packed. */
+LD_API int ld_fbank_reset_mel(ld_ctx* ctx);
 
 /* Replaces model.load_state_dict(checkpoint['state_dict']); model.eval() (segment_laughter.py:63-72):
  * folds every BatchNorm's running statistics into a per-channel scale/shift and repacks the conv

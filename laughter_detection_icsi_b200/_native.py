@@ -14,6 +14,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libld_b200.so")
 
 LD_PREPROC_UTTERANCE = 0
 LD_PREPROC_FRAME = 1
+LD_PRECISION_FP16 = 0
+LD_PRECISION_SPLIT = 1
+PRECISIONS = {"fp16": LD_PRECISION_FP16, "split": LD_PRECISION_SPLIT}
 TIMING_CLASSES = ("conv_gemm", "stem", "head", "fbank", "segment")
 
 
@@ -30,7 +33,8 @@ class LdConfig(ctypes.Structure):
         ("linear_layer_size", c_int32),
         ("chunk_rows", c_int32),
         ("fbank_preproc", c_int32),
-        ("reserved", c_int32 * 6),
+        ("precision", c_int32),
+        ("reserved", c_int32 * 5),
     ]
 
 
@@ -47,6 +51,7 @@ SIGNATURES = {
     "ld_destroy": (None, [c_void_p]),
     "ld_fbank_i16": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_void_p, POINTER(c_int64), c_void_p]),
     "ld_fbank_num_frames": (c_int64, [c_int64]),
+    "ld_fbank_reset_mel": (c_int, [c_void_p]),
     "ld_resnet_load_weights": (c_int, [c_void_p, POINTER(LdTensor), c_int32]),
     "ld_resnet_infer_windows": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_void_p]),
     "ld_segment_runs": (c_int, [c_void_p, c_void_p, c_int32, POINTER(c_int64), c_int32, POINTER(c_double), POINTER(c_double),

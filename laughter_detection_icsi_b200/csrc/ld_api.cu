@@ -69,6 +69,45 @@ struct DeviceBuf {
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
+// Pinned host staging for the small tables a call uploads (channel offsets, thresholds): a ring of slots, each guarded by an
+// event recorded after the copy that reads it, so that the steady state neither allocates nor synchronises the stream.
+struct StagingRing {
+    static constexpr int kSlots = 16;
+    void* host[kSlots] = {};
+    size_t cap[kSlots] = {};
+    cudaEvent_t ev[kSlots] = {};
+    int next = 0;
+    // copies `bytes` from `src` (any host memory) to device memory `dst` on `stream` without blocking on the stream
+    int upload(void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+        const int s = next;
+        next = (next + 1) % kSlots;
+        cudaError_t e = cudaSuccess;
+        if (!ev[s]) e = cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventSynchronize(ev[s]);   // the copy that last used this slot (16 uploads ago) is done
+        if (e == cudaSuccess && cap[s] < bytes) {
+            if (host[s]) cudaFreeHost(host[s]);
+            host[s] = nullptr; cap[s] = 0;
+            const size_t want = bytes < 4096 ? 4096 : bytes;
+            e = cudaMallocHost(&host[s], want);
+            if (e == cudaSuccess) cap[s] = want;
+        }
+        if (e == cudaSuccess) {
+            std::memcpy(host[s], src, bytes);
+            e = cudaMemcpyAsync(dst, host[s], bytes, cudaMemcpyHostToDevice, stream);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(ev[s], stream);
+        if (e != cudaSuccess) return fail(LD_ERR_CUDA, std::string("staging upload: ") + cudaGetErrorString(e));
+        return LD_OK;
+    }
+    void release() {
+        for (int i = 0; i < kSlots; ++i) {
+            if (host[i]) cudaFreeHost(host[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+            host[i] = nullptr; ev[i] = nullptr; cap[i] = 0;
+        }
+    }
+};
+
 }  // namespace
 
 struct ld_ctx {
@@ -95,6 +134,8 @@ struct ld_ctx {
     // fbank
     float* fbank_tables = nullptr;
     std::vector<float> mel_host;
+    const float* mel_key = nullptr;   // device pointer the sparse filterbank below was packed from (ld_fbank_i16)
+    StagingRing staging;
     DeviceBuf mel_sparse;  // weights | lo | len | off
     ld::FbankMel mel{};
     unsigned long long* pcm_sum = nullptr;
@@ -147,6 +188,10 @@ int validate_config(const ld_config& c) {
         if (c.filter_sizes[i] % 16 != 0 || c.filter_sizes[i] < 16 || c.filter_sizes[i] > 64)
             return fail(LD_ERR_UNSUPPORTED, "filter_sizes must be multiples of 16 in [16, 64]");
     if (c.filter_sizes[0] != 64) return fail(LD_ERR_UNSUPPORTED, "block1 must keep 64 channels (identity shortcut)");
+    // AvgPool2d(4) of the 13 x 6 block4 output leaves 3 x 1 positions per channel (models.py:229-231): the reference raises a shape
+    // error in bn2 for any other linear_layer_size
+    if (c.linear_layer_size != c.filter_sizes[3] * 3)
+        return fail(LD_ERR_INVALID, "linear_layer_size must equal filter_sizes[3] * 3 for 100 x 44 windows");
     return LD_OK;
 }
 
@@ -160,9 +205,9 @@ int upload_channel_table(ld_ctx* ctx, const int64_t* frames, int n_chan, int gap
         so += frames[c] + gap; fo += frames[c];
     }
     seq_total = so; feat_total = fo;
+    // the device table is written in stream order, so a later call's upload cannot overtake this call's kernels
     if (int r = ctx->chan_table.ensure(h.size() * sizeof(long long))) return r;
-    LD_CUDA(cudaMemcpyAsync(ctx->chan_table.p, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice, stream));
-    LD_CUDA(cudaStreamSynchronize(stream));  // h is a stack-owned staging vector
+    if (int r = ctx->staging.upload(ctx->chan_table.p, h.data(), h.size() * sizeof(long long), stream)) return r;
     const long long* d = static_cast<const long long*>(ctx->chan_table.p);
     ct.seq_off = d; ct.frames = d + n_chan; ct.feat_off = d + 2 * n_chan; ct.n_chan = n_chan;
     return LD_OK;
@@ -477,6 +522,7 @@ void ld_destroy(ld_ctx* ctx) {
     if (ctx->head_params) cudaFree(ctx->head_params);
     if (ctx->fbank_tables) cudaFree(ctx->fbank_tables);
     if (ctx->pcm_sum) cudaFree(ctx->pcm_sum);
+    ctx->staging.release();
     ctx->mel_sparse.release(); ctx->chan_table.release(); ctx->seg_scratch.release(); ctx->iir_scratch.release();
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -587,8 +633,9 @@ int ld_fbank_i16(ld_ctx* ctx, const int16_t* pcm_d, const int64_t* chan_len, int
     LD_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const int F = ctx->cfg.num_filters;
-    // sparse view of the filterbank (rebuilt only when the matrix changes)
-    {
+    // sparse view of the filterbank: packed when the caller passes a different matrix (pointer) than the last call did, or after
+    // ld_fbank_reset_mel; the steady state has no D2H copy and no stream synchronisation (see include/ld_b200.h)
+    if (mel_d != ctx->mel_key) {
         std::vector<float> m(257 * static_cast<size_t>(F));
         LD_CUDA(cudaMemcpyAsync(m.data(), mel_d, m.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
         LD_CUDA(cudaStreamSynchronize(stream));
@@ -616,6 +663,7 @@ int ld_fbank_i16(ld_ctx* ctx, const int16_t* pcm_d, const int64_t* chan_len, int
             ctx->mel.lo = di; ctx->mel.len = di + F; ctx->mel.off = di + 2 * F; ctx->mel.n_filters = F;
             ctx->mel_host = m;
         }
+        ctx->mel_key = mel_d;
     }
     const int per_frame = ctx->cfg.fbank_preproc == LD_PREPROC_FRAME;
     long long s_off = 0, f_off = 0;
@@ -633,6 +681,12 @@ int ld_fbank_i16(ld_ctx* ctx, const int16_t* pcm_d, const int64_t* chan_len, int
     return LD_OK;
 }
 
+int ld_fbank_reset_mel(ld_ctx* ctx) {
+    if (!ctx) return fail(LD_ERR_INVALID, "ctx is null");
+    ctx->mel_key = nullptr;
+    return LD_OK;
+}
+
 int ld_segment_runs(ld_ctx* ctx, const void* probs_d, int32_t prob_is_f64, const int64_t* chan_frames, int32_t n_chan,
                     const double* thr_cmp, const double* thr_raw, int32_t n_thr, int32_t* starts_d, int32_t* ends_d,
                     int32_t* chan_d, int32_t* counts_d, int32_t cap, void* stream_v) {
@@ -647,9 +701,12 @@ int ld_segment_runs(ld_ctx* ctx, const void* probs_d, int32_t prob_is_f64, const
     if (total >= (1ll << 31)) return fail(LD_ERR_UNSUPPORTED, "more than 2^31 frames in one call");
     if (int r = ctx->thr_buf.ensure(2 * sizeof(double) * n_thr)) return r;
     double* thr_d = static_cast<double*>(ctx->thr_buf.p);
-    LD_CUDA(cudaMemcpyAsync(thr_d, thr_cmp, sizeof(double) * n_thr, cudaMemcpyHostToDevice, stream));
-    LD_CUDA(cudaMemcpyAsync(thr_d + n_thr, thr_raw, sizeof(double) * n_thr, cudaMemcpyHostToDevice, stream));
-    LD_CUDA(cudaStreamSynchronize(stream));
+    {
+        std::vector<double> thr(2 * static_cast<size_t>(n_thr));
+        std::memcpy(thr.data(), thr_cmp, sizeof(double) * n_thr);
+        std::memcpy(thr.data() + n_thr, thr_raw, sizeof(double) * n_thr);
+        if (int r = ctx->staging.upload(thr_d, thr.data(), thr.size() * sizeof(double), stream)) return r;
+    }
     if (int r = ctx->seg_scratch.ensure(ld::segment_scratch_ints(total, n_thr) * sizeof(int))) return r;
     Timed t(ctx, stream, 4, 3);
     LD_CUDA(ld::launch_segment_runs(probs_d, prob_is_f64, ct, total, thr_d, thr_d + n_thr, n_thr, starts_d, ends_d, chan_d,
@@ -714,7 +771,11 @@ int ld_infer_pcm_host(ld_ctx* ctx, const int16_t* pcm_host, const int64_t* chan_
     if (int r = ctx->e2e_probs.ensure(frames * sizeof(float))) return r;
     if (int r = ctx->e2e_mel.ensure(257 * F * sizeof(float))) return r;
     LD_CUDA(cudaMemcpyAsync(ctx->e2e_pcm.p, pcm_host, samples * sizeof(int16_t), cudaMemcpyHostToDevice, stream));
-    LD_CUDA(cudaMemcpyAsync(ctx->e2e_mel.p, mel_host, 257 * F * sizeof(float), cudaMemcpyHostToDevice, stream));
+    if (ctx->mel_key != ctx->e2e_mel.p || ctx->mel_host.size() != 257 * static_cast<size_t>(F) ||
+        std::memcmp(ctx->mel_host.data(), mel_host, ctx->mel_host.size() * sizeof(float)) != 0) {
+        LD_CUDA(cudaMemcpyAsync(ctx->e2e_mel.p, mel_host, 257 * F * sizeof(float), cudaMemcpyHostToDevice, stream));
+        ctx->mel_key = nullptr;   // same device buffer, new contents: repack the sparse filterbank
+    }
     if (int r = ld_fbank_i16(ctx, static_cast<const int16_t*>(ctx->e2e_pcm.p), chan_len, n_chan,
                              static_cast<const float*>(ctx->e2e_mel.p), static_cast<float*>(ctx->e2e_feats.p), nullptr, stream_v))
         return r;

@@ -225,15 +225,15 @@ cudaError_t launch_pcm_sum(const int16_t* pcm, long long n, unsigned long long* 
 cudaError_t launch_fbank(const int16_t* pcm, long long n_samples, long long n_frames, const unsigned long long* sum_biased,
                          int per_frame, const FbankMel& mel, const float* tables, float* feats, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (!attr_set.flag()) {
         cudaError_t e = cudaFuncSetAttribute(fbank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(FbankSmem)));
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(fbank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(sizeof(FbankSmem)));
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set.flag() = true;
     }
     const unsigned grid = static_cast<unsigned>((n_frames + kFramesPerCta * kGroupsPerCta - 1) / (kFramesPerCta * kGroupsPerCta));
     if (per_frame)

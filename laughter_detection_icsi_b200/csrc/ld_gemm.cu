@@ -464,12 +464,12 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
 // Host launcher.
 template <int CIN, int COUT, int MODE>
 static cudaError_t launch_typed(const GemmLaunch& h, int m_tiles, int M, int num_sms, cudaStream_t stream) {
-    static bool attr_set = false;
+    static PerDeviceOnce attr_set;
     const GemmSmem lay = gemm_smem_layout(CIN, COUT, h.n_wtaps, h.n_jobs, h.ext_alloc, h.groups_per_stage, h.n_stages);
-    if (!attr_set) {
+    if (!attr_set.flag()) {
         cudaError_t e = cudaFuncSetAttribute(gemm_taps_kernel<CIN, COUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set.flag() = true;
     }
     const long long total = static_cast<long long>(m_tiles) * h.n_jobs;
     if (total <= 0) return cudaSuccess;

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include <cuda_fp16.h>
+#include <cuda_runtime.h>
 
 namespace ld {
 
@@ -26,6 +27,17 @@ constexpr int kMaxOuts = 8;      // output planes per job (their accumulators si
 constexpr int kTmemCols = 512;   // accumulator columns per SM, split into n_issuers stages: n_outs * cout <= 512 / n_issuers
 constexpr int kMaxJobs = 16;     // jobs per launch (the planner also splits a layer into launches of at most this many output planes)
 constexpr int kGuardRows = 104;  // zero guard rows allocated before/after every plane
+
+// cudaFuncSetAttribute applies to the CURRENT device only: one flag per device, so that a second context on another GPU of the
+// same process configures its kernels too.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool& flag() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return done[d & 63];
+    }
+};
 
 enum OutMode : int32_t { OUT_PLAIN = 0, OUT_COLSPLIT = 1 };
 

@@ -154,11 +154,11 @@ wgrad_mma_kernel(const __grid_constant__ WgradLaunch L) {
 
 template <int CIN, int COUT>
 static cudaError_t launch_wg(const WgradLaunch& L, int num_sms, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (!attr_set.flag()) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_mma_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set.flag() = true;
     }
     const long long tiles = (L.M + kWgTile - 1) / kWgTile;
     if (tiles <= 0) return cudaSuccess;

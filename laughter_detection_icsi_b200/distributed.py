@@ -37,6 +37,78 @@ def gather_results(local_results, unit_ids, n_units, dst=0):
     return [merged[i] for i in range(n_units)]
 
 
+def pack_segments(local_results, settings):
+    """Per-unit instance dicts {(thr, min_len): (n, 2) float64 array} -> (counts int64 [units, settings], data float64 [total, 2]):
+    two flat buffers instead of pickled Python objects, so the final gather moves raw bytes."""
+    import numpy as np
+    counts = np.zeros((len(local_results), len(settings)), dtype=np.int64)
+    parts = []
+    for u, res in enumerate(local_results):
+        for k, key in enumerate(settings):
+            a = np.asarray(res[key], dtype=np.float64).reshape(-1, 2)
+            counts[u, k] = len(a)
+            parts.append(a)
+    data = np.concatenate(parts) if parts else np.zeros((0, 2), dtype=np.float64)
+    return counts, data
+
+
+def unpack_segments(counts, data, settings):
+    out, off = [], 0
+    for u in range(counts.shape[0]):
+        d = {}
+        for k, key in enumerate(settings):
+            n = int(counts[u, k])
+            d[key] = data[off:off + n]
+            off += n
+        out.append(d)
+    return out
+
+
+def gather_segments(local_results, unit_ids, n_units, settings, dst=0):
+    """The final gather of multi-GPU inference: every rank's per-unit segment lists end up on `dst`, ordered by unit index
+    (None elsewhere).  Buffers travel as tensors (NCCL: staged through the GPU over NVLink; gloo: host tensors): sizes
+    first (one small all_gather), then one gather of the padded flat buffers."""
+    import numpy as np
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        merged = dict(zip(unit_ids, local_results))
+        return [merged[i] for i in range(n_units)]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    on_gpu = dist.get_backend() == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    counts, data = pack_segments(local_results, settings)
+    sizes = torch.tensor([len(unit_ids), data.shape[0]], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = [tuple(int(x) for x in t.tolist()) for t in all_sizes]
+    max_units, max_rows = max(s[0] for s in all_sizes), max(s[1] for s in all_sizes)
+    n_set = len(settings)
+    # one int64 buffer per rank: unit ids | counts | segment data (float64 bit patterns)
+    width = max_units * (1 + n_set) + 2 * max_rows
+    buf = np.zeros(width, dtype=np.int64)
+    buf[:len(unit_ids)] = unit_ids
+    buf[max_units:max_units + counts.size] = counts.reshape(-1)
+    buf[max_units * (1 + n_set):max_units * (1 + n_set) + data.size] = data.reshape(-1).view(np.int64)
+    t = torch.from_numpy(buf)
+    t = t.pin_memory().to(dev, non_blocking=True) if on_gpu else t
+    out = [torch.empty(width, dtype=torch.int64, device=dev) for _ in range(world)] if rank == dst else None
+    dist.gather(t, out, dst=dst)
+    if rank != dst:
+        return None
+    merged = {}
+    for r, part in enumerate(out):
+        n_u, n_rows = all_sizes[r]
+        a = part.cpu().numpy()
+        ids = a[:n_u]
+        cnt = a[max_units:max_units + n_u * n_set].reshape(n_u, n_set)
+        seg = a[max_units * (1 + n_set):max_units * (1 + n_set) + 2 * n_rows].view(np.float64).reshape(n_rows, 2)
+        for uid, res in zip(ids.tolist(), unpack_segments(cnt, seg, settings)):
+            merged[uid] = res
+    missing = [i for i in range(n_units) if i not in merged]
+    if missing:
+        raise RuntimeError(f"units {missing} were not processed by any rank")
+    return [merged[i] for i in range(n_units)]
+
+
 def allreduce_gradients(params, world_size=None):
     """Data-parallel gradient averaging for training: the gradients of all parameters travel as ONE
     flat fp32 bucket (221 217 elements = 0.88 MB for resnet_base), summed over ranks with a single all-reduce (NCCL over

@@ -58,13 +58,16 @@ class Engine:
     """One ld_ctx on one CUDA device."""
 
     def __init__(self, device=0, chunk_rows=0, fbank_preproc=_native.LD_PREPROC_UTTERANCE, filter_sizes=(64, 32, 16, 16),
-                 linear_layer_size=48):
+                 linear_layer_size=48, precision="fp16"):
         self.lib = _native.load_library()
         if not torch.cuda.is_available():
             raise LdError("no CUDA device: the B200 kernels cannot run and there is no CPU fallback")
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        if precision not in _native.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_native.PRECISIONS)}")
+        self.precision = precision
         self.cfg = _native.default_config(chunk_rows=chunk_rows, fbank_preproc=fbank_preproc, filter_sizes=filter_sizes,
-                                          linear_layer_size=linear_layer_size)
+                                          linear_layer_size=linear_layer_size, precision=_native.PRECISIONS[precision])
         torch.cuda.init()
         with torch.cuda.device(self.device):
             torch.zeros(1, device=self.device)  # make sure the primary context exists
@@ -156,6 +159,8 @@ class Engine:
         if pcm_host.dtype != torch.int16 or pcm_host.is_cuda:
             raise ValueError("pcm_host must be an int16 host tensor")
         chan_len = [int(x) for x in chan_len]
+        if sum(chan_len) != pcm_host.numel():
+            raise ValueError("chan_len does not add up to the number of samples")
         frames = [int(self.lib.ld_fbank_num_frames(n)) for n in chan_len]
         probs = torch.empty(sum(frames), dtype=torch.float32, pin_memory=True)
         m = self.mel_device(mel).cpu().contiguous()
@@ -171,6 +176,8 @@ class Engine:
             raise ValueError("probs must be a float32/float64 CUDA tensor")
         probs = probs.contiguous().reshape(-1)
         chan_frames = [probs.numel()] if chan_frames is None else [int(x) for x in chan_frames]
+        if sum(chan_frames) != probs.numel():
+            raise ValueError("chan_frames does not add up to the number of probabilities")
         thr_raw = thr_cmp if thr_raw is None else thr_raw
         n_thr = len(thr_cmp)
         cap = int(cap) if cap else max(1024, probs.numel() // 64)
@@ -345,6 +352,10 @@ class Engine:
     def kernel_launches(self):
         return int(self.lib.ld_kernel_launches(self._h))
 
+    @property
+    def train_kernel_launches(self):
+        return int(self.lib.ld_train_kernel_launches(self._h))
+
 
 _engines = {}
 
@@ -352,7 +363,8 @@ _engines = {}
 def get_engine(device=0, **kw):
     """Process-wide engine per device (one context per GPU per process)."""
     idx = device if isinstance(device, int) else (torch.device(device).index or 0)
-    full = dict(chunk_rows=0, fbank_preproc=_native.LD_PREPROC_UTTERANCE, filter_sizes=(64, 32, 16, 16), linear_layer_size=48)
+    full = dict(chunk_rows=0, fbank_preproc=_native.LD_PREPROC_UTTERANCE, filter_sizes=(64, 32, 16, 16), linear_layer_size=48,
+                precision="fp16")
     full.update(kw)
     full["filter_sizes"] = tuple(int(f) for f in full["filter_sizes"])
     kw = full

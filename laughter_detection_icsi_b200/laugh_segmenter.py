@@ -54,7 +54,11 @@ def lowpass(sig, filter_order=2, cutoff=0.01):
 
 
 def _device_of(x):
-    return x.device.index or 0 if torch.is_tensor(x) and x.is_cuda else 0
+    """The GPU the work runs on: the tensor's own device, else the process's CURRENT device (a rank whose model lives on
+    cuda:k must not create a second context on GPU 0)."""
+    if torch.is_tensor(x) and x.is_cuda:
+        return x.device.index or 0
+    return torch.cuda.current_device() if torch.cuda.is_available() else 0
 
 
 def _to_device(probs, eng):

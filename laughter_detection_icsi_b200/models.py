@@ -83,6 +83,16 @@ class ResNetBigger(nn.Module):
     def _fingerprint(self):
         return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
 
+    def train(self, mode=True):
+        self._ld_fingerprint = None   # parameters usually changed between a training phase and the next eval forward
+        return super().train(mode)
+
+    def mark_weights_dirty(self):
+        """Call after writing parameters or BatchNorm buffers through raw pointers / ``.data`` (ld_clip_adam_step,
+        init_weights): such writes do not bump ``tensor._version``, so the fingerprint below would not see them and the next
+        eval forward would run on stale folded weights."""
+        self._ld_fingerprint = None
+
     def b200_engine(self):
         """The process-wide ld_ctx of the device the parameters live on, with these weights loaded."""
         p = self.conv1.weight
@@ -131,6 +141,7 @@ class ResNetBigger(nn.Module):
             off += n
         self._ld_flat, self._ld_flat_offsets = flat, offsets
         self._ld_flat_leaves = []
+        self._ld_fingerprint = None   # storage moved: re-fold on the next eval forward
         return flat
 
     def flat_gradient(self):

@@ -14,16 +14,23 @@ from . import laugh_segmenter
 class LaughterPipeline:
     def __init__(self, state_dict, device=0, thresholds=(0.5,), min_lengths=(0.2,), mel="lhotse", **engine_kw):
         self.engine = _engine.get_engine(device, **engine_kw)
-        self.engine.load_state_dict(state_dict)
-        self.engine.weights_owner = self
+        self._state_dict = {k: v.detach().clone() for k, v in state_dict.items() if torch.is_tensor(v)}
+        self._ensure_weights()
         self.thresholds = [float(t) for t in thresholds]
         self.min_lengths = [float(m) for m in min_lengths]
         self.mel = mel
         self._cap = None
 
+    def _ensure_weights(self):
+        """The engine is shared per device: another pipeline / model may have loaded its own checkpoint since."""
+        if self.engine.weights_owner is not self:
+            self.engine.load_state_dict(self._state_dict)
+            self.engine.weights_owner = self
+
     # --- device-resident stages ------------------------------------------------------------------------
     def probabilities(self, pcm_dev, chan_len):
         """int16 CUDA PCM (channels end to end) -> (float32 CUDA probs, frames per channel)."""
+        self._ensure_weights()
         feats, frames = self.engine.fbank(pcm_dev, chan_len, mel=self.mel)
         return self.engine.infer_windows(feats, frames), frames
 

@@ -15,6 +15,8 @@ def init_weights(model):
     # every parameter, BatchNorm affine and biases included, ~ N(0, 0.01)
     for _, param in model.named_parameters():
         nn.init.normal_(param.data, mean=0, std=0.01)
+    if hasattr(model, "mark_weights_dirty"):
+        model.mark_weights_dirty()   # writes through .data do not bump tensor._version (models.ResNetBigger.b200_engine)
 
 
 def save_checkpoint(state, is_best, checkpoint):

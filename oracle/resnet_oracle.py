@@ -120,6 +120,20 @@ def window_probs(sd, feats, batch_size=32, dtype=torch.float32, start=0, stop=No
     return torch.cat(out).numpy()
 
 
+def window_probs_autograd(sd, feats, batch_size=32):
+    """window_probs the way the reference literally runs it: segment_laughter.py:95 calls ``model(x).cpu().detach()`` WITHOUT
+    torch.no_grad(), so every batch builds (and drops) an autograd graph over parameters that require grad.  Same
+    numbers, more CPU time -- used by bench.py's CPU baseline only."""
+    feats = np.asarray(feats, dtype=np.float32)
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v) for k, v in sd.items()}
+    out = []
+    for i0 in range(0, len(feats), batch_size):
+        idx = range(i0, min(len(feats), i0 + batch_size))
+        x = torch.from_numpy(np.stack([window(feats, i) for i in idx]))[:, None]
+        out.append(forward(sd, x).detach().reshape(-1))
+    return torch.cat(out).numpy()
+
+
 def calibrate_head(sd, feats, n_windows=512, target_std=2.0):
     """Rescale linear2 so that logits over the first windows have mean 0 / std `target_std`: a random-init
     network otherwise emits probabilities in a ~1e-3 wide band around 0.5."""

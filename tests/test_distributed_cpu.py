@@ -81,4 +81,41 @@ def test_train_mirror_helpers():
     acc, prec, rec = ld_train._calc_metrics(torch.tensor([0.9, 0.2, 0.8, 0.4]), torch.tensor([1.0, 0.0, 0.0, 1.0]))
     assert (acc, prec, rec) == (0.5, 0.5, 0.5)
     args = ld_train.build_parser().parse_args(["--config", "resnet_base", "--checkpoint_dir", "ck"])
-    assert args.num_epochs == 1 and args.dropout_rate == 0.5 and args.gradient_accumulation_steps == 1
+    # string-typed numerics like the reference's argparse (train.py:68-117)
+    assert args.num_epochs == 1 and args.dropout_rate == '0.5' and args.gradient_accumulation_steps == '1' and args.lhotse_dir == 'lhotse'
+
+
+def _seg_worker(rank, world, port, out_path):
+    import numpy as np
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    settings = [(0.5, 0.0), (0.5, 0.2), (0.9, 0.0)]
+    durations = [5.0, 1.0, 3.0, 2.0, 4.0, 6.0, 0.5]
+    mine = ldd.shard_units(durations, world)[rank]
+
+    def result(u):   # unit u: u segments for the first setting, one for the second, none for the third
+        return {settings[0]: np.array([[u + 0.125 * i, u + 0.125 * i + 0.1] for i in range(u)], dtype=np.float64).reshape(-1, 2),
+                settings[1]: np.array([[float(u), u + 0.5]]), settings[2]: np.zeros((0, 2))}
+    merged = ldd.gather_segments([result(u) for u in mine], mine, len(durations), settings, dst=0)
+    if rank == 0:
+        ok = all(np.array_equal(merged[u][k], result(u)[k]) for u in range(len(durations)) for k in settings)
+        torch.save({"ok": ok, "n": len(merged)}, out_path)
+    else:
+        assert merged is None
+    dist.destroy_process_group()
+
+
+def test_two_rank_segment_gather_as_flat_buffers(tmp_path):
+    """The final gather of corpus-shaped inference (bench.py --config corpus): packed int64/float64 buffers, not pickles."""
+    out = str(tmp_path / "seg.pt")
+    mp.spawn(_seg_worker, args=(2, 29331 + os.getpid() % 500, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["ok"] and r["n"] == 7
+    import numpy as np
+    settings = [(0.5, 0.2)]
+    single = ldd.gather_segments([{settings[0]: np.array([[1.0, 2.0]])}], [0], 1, settings)
+    assert np.array_equal(single[0][settings[0]], np.array([[1.0, 2.0]]))
+    c, d = ldd.pack_segments([{settings[0]: np.zeros((0, 2))}, {settings[0]: np.array([[0.5, 0.75]])}], settings)
+    assert c.tolist() == [[0], [1]] and d.tolist() == [[0.5, 0.75]]
+    back = ldd.unpack_segments(c, d, settings)
+    assert back[0][settings[0]].shape == (0, 2) and back[1][settings[0]].tolist() == [[0.5, 0.75]]

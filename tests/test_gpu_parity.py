@@ -310,6 +310,80 @@ def test_full_size_channel_properties(engine):
     assert np.abs(probs[59800:].cpu().numpy() - ref).max() < 2e-2
 
 
+def test_default_chunk_rows_is_the_benchmarked_configuration():
+    """bench.py and the CLI run chunk_rows=0 (32 768 window starts per pass of the conv stack, 66 passes per 6-channel-hour
+    step).  Three ragged channels, 71 014 frames: (a) bit-equal to the chunk_rows=2048 engine everywhere, (b) within the
+    precision budget of the fp64 oracle on the windows that straddle a pass boundary (sequence rows 32 768 and 65 536), a
+    channel boundary (tail windows of one channel, first windows of the next) and the tail of the last channel -- for the
+    calibrated bench checkpoint AND random-init weights (1e-3, BASELINE.json)."""
+    from laughter_detection_icsi_b200.engine import get_engine
+    big, small = get_engine(0), get_engine(0, chunk_rows=2048)
+    assert big.cfg.chunk_rows == 0
+    T = [30011, 5003, 36000]
+    pcm = torch.cat([synth.synth_channel(t * 160, meeting=9, channel=c, device="cuda") for c, t in enumerate(T)])
+    feats, frames = big.fbank(pcm, [t * 160 for t in T])
+    assert frames == T
+    # sequence row of frame f of channel c = f + sum_{c' < c} (T[c'] + 100): pass boundaries in channel frames
+    seq0 = np.cumsum([0] + [t + 100 for t in T[:-1]])
+    spots = []
+    for boundary in (32768, 65536):
+        c = int(np.searchsorted(seq0, boundary, side="right") - 1)
+        f = boundary - int(seq0[c])
+        assert 120 < f < T[c] - 120, "the pass boundary must fall inside a channel for this test to mean anything"
+        spots.append((c, f - 110, f + 12))          # windows whose 100 rows straddle the boundary, and a few either side
+    spots += [(0, T[0] - 105, T[0]), (1, 0, 12), (1, T[1] - 12, T[1]), (2, 0, 8), (2, T[2] - 105, T[2])]
+    off = np.cumsum([0] + T)
+    f_host = feats.cpu().numpy()
+    for sd, tol in ((synth.synthetic_state_dict(), 2e-2), (resnet_oracle.random_state_dict(seed=5), PROB_ATOL)):
+        small.load_state_dict(sd); small.weights_owner = None
+        big.load_state_dict(sd); big.weights_owner = None
+        p_big = big.infer_windows(feats, T)
+        p_small = small.infer_windows(feats, T)
+        assert torch.equal(p_big, p_small), "chunking changed the probabilities"
+        got = p_big.cpu().numpy()
+        for c, a, b in spots:
+            chan = f_host[off[c]:off[c + 1]]
+            ref = resnet_oracle.window_probs(sd, chan, dtype=torch.float64, start=a, stop=b)
+            assert np.abs(got[off[c] + a:off[c] + b] - ref).max() < tol, (c, a, b)
+
+
+def test_inference_dataloader_generator_form(tmp_path):
+    """The reference's own loop (segment_laughter.py:90-100): for model_inputs in create_inference_dataloader(path):
+    model(model_inputs[:, None].float().to(device)) in batches of 32 -- same probabilities as the fused fast path."""
+    import scipy.io.wavfile
+    from laughter_detection_icsi_b200 import load_data
+    pcm = synth.synth_channel(16000 * 3 + 55, meeting=5, channel=0).numpy()
+    wav = tmp_path / "a.wav"
+    scipy.io.wavfile.write(str(wav), 16000, pcm)
+    m = models.ResNetBigger(dropout_rate=0.0, linear_layer_size=48, filter_sizes=[64, 32, 16, 16])
+    m.load_state_dict(synth.synthetic_state_dict())
+    m.set_device("cuda")
+    m.eval()
+    loader = load_data.create_inference_dataloader(str(wav))
+    probs, n_batches = [], 0
+    for model_inputs in loader:
+        assert model_inputs.shape[1:] == (100, 44) and model_inputs.shape[0] <= 32
+        x = model_inputs[:, None, :, :].float().to("cuda")
+        preds = m(x).cpu().detach().numpy().squeeze()
+        probs += [float(preds)] if preds.ndim == 0 else list(preds)
+        n_batches += 1
+    fused = load_data.infer_audio_file(str(wav), m)
+    assert len(probs) == len(fused) == (len(pcm) + 80) // 160 and n_batches == -(-len(fused) // 32)
+    assert np.array_equal(np.asarray(probs, dtype=np.float32), fused)   # same kernels, same arithmetic: bit-identical
+
+
+def test_two_pipelines_share_the_engine_without_mixing_weights():
+    """the engine is process-wide per device; every pipeline re-loads its own checkpoint when another owner
+    loaded one in between."""
+    a = LaughterPipeline(synth.synthetic_state_dict(), device=0, chunk_rows=2048)
+    pcm = synth.synth_channel(16000 * 2, meeting=6).cuda()
+    pa, _ = a.probabilities(pcm, [pcm.numel()])
+    b = LaughterPipeline(resnet_oracle.random_state_dict(seed=8), device=0, chunk_rows=2048)
+    pb, _ = b.probabilities(pcm, [pcm.numel()])
+    pa2, _ = a.probabilities(pcm, [pcm.numel()])
+    assert torch.equal(pa, pa2) and not torch.equal(pa, pb)
+
+
 def test_segment_laughter_cli_end_to_end(tmp_path):
     """The reference's command line (segment_laughter.py:28-52,199) on a synthetic WAV and checkpoint directory:
     TextGrid tree output_dir/t_<thr>/l_<min_l>/<basename>.TextGrid with the segments the oracle finds on the same
