@@ -138,7 +138,7 @@ def plan_plane_bytes_per_row(cfg=None, conv=None):
     the algorithmic traffic figure behind bench.py's HBM roofline.  `conv` restricts the sum to the
     launches of one conv layer (e.g. "block1.1.conv2")."""
     plan = plan_json(cfg)
-    size = {p["id"]: 2 * p["wp"] * p["C"] for p in plan["planes"]}
+    size = {p["id"]: 2 * p["wp"] * p["C"] * (2 if p.get("split") else 1) for p in plan["planes"]}   # [hi | lo] planes count twice
     total = 0
     for c in plan["convs"]:
         if conv is not None and c["conv"] != conv:

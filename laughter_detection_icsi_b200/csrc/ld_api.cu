@@ -46,6 +46,9 @@ struct ConvWeights {
     float* shift = nullptr;
     int cin = 0, cout = 0, ksize = 0;
     bool has_res = false;  // the launches of this conv add a residual: one extra identity weight slab
+    bool split_in = false, split_w = false;  // split precision: [hi | lo] input channels / hi + lo weight blocks
+    int cin_eff() const { return cin * (split_in ? 2 : 1); }
+    int n_slabs() const { return ksize * ksize * (split_w ? 2 : 1) + (has_res ? 1 : 0); }
     std::string conv, bn;
 };
 
@@ -179,6 +182,7 @@ void config_to_net(const ld_config& c, ld::NetConfig& n) {
     n.H = c.num_frames; n.W = c.num_filters;
     for (int i = 0; i < 4; ++i) n.filters[i] = c.filter_sizes[i];
     n.linear_in = c.linear_layer_size;
+    n.precision = c.precision;
 }
 
 int validate_config(const ld_config& c) {
@@ -188,6 +192,10 @@ int validate_config(const ld_config& c) {
         if (c.filter_sizes[i] % 16 != 0 || c.filter_sizes[i] < 16 || c.filter_sizes[i] > 64)
             return fail(LD_ERR_UNSUPPORTED, "filter_sizes must be multiples of 16 in [16, 64]");
     if (c.filter_sizes[0] != 64) return fail(LD_ERR_UNSUPPORTED, "block1 must keep 64 channels (identity shortcut)");
+    if (c.precision != LD_PRECISION_FP16 && c.precision != LD_PRECISION_SPLIT) return fail(LD_ERR_INVALID, "unknown ld_precision");
+    if (c.precision == LD_PRECISION_SPLIT)
+        for (int i = 1; i < 4; ++i)
+            if (c.filter_sizes[i] > 32) return fail(LD_ERR_UNSUPPORTED, "split precision needs filter_sizes[1..3] <= 32 ([hi | lo] planes of <= 64 channels)");
     // AvgPool2d(4) of the 13 x 6 block4 output leaves 3 x 1 positions per channel (models.py:229-231): the reference raises a shape
     // error in bn2 for any other linear_layer_size
     if (c.linear_layer_size != c.filter_sizes[3] * 3)
@@ -300,14 +308,20 @@ int64_t ld_gemm_program_json(const ld_config* cfg, char* buf, int64_t cap) {
             for (const auto& other : plan.convs)
                 if (other.conv == cs.conv)
                     for (const auto& js : other.jobs) has_res = has_res || js.res_plane >= 0;
-            L.cin = cs.cin; L.cout = cs.cout; L.n_wtaps = cs.ksize * cs.ksize + (has_res ? 1 : 0);
+            const int kk = cs.ksize * cs.ksize, n_slabs = kk * (cs.split_w ? 2 : 1) + (has_res ? 1 : 0);
+            L.cin = cs.cin * (cs.split_in ? 2 : 1); L.cout = cs.cout; L.n_wtaps = n_slabs;
             L.relu = cs.relu; L.wp = cs.wp; L.out_mode = cs.out_mode; L.wp2 = cs.wp2; L.hp = cs.hp;
             L.w_stack = cs.ksize == 3 ? 1 : 0;
+            L.w_blocks = cs.ksize == 3 ? (cs.split_w ? 2 : 1) : 0;
+            L.split_out = cs.split_out;
             std::vector<ld::HostJob> jobs(cs.jobs.size());
             for (size_t j = 0; j < cs.jobs.size(); ++j) {
                 const auto& js = cs.jobs[j];
-                for (const auto& t : js.taps) jobs[j].taps.push_back({fake(t.plane), 0, t.shift, t.wtap});
-                if (js.res_plane >= 0) jobs[j].taps.push_back({fake(js.res_plane), 0, js.res_shift, cs.ksize * cs.ksize});
+                for (const auto& t : js.taps) {
+                    jobs[j].taps.push_back({fake(t.plane), 0, t.shift, t.wtap, 0});
+                    if (cs.split_w) jobs[j].taps.push_back({fake(t.plane), 0, t.shift, kk + t.wtap, cs.split_in ? 1 : 0});
+                }
+                if (js.res_plane >= 0) jobs[j].taps.push_back({fake(js.res_plane), 0, js.res_shift, n_slabs - 1, 0});
                 jobs[j].out0 = fake(js.out0);
                 jobs[j].out1 = js.out1 >= 0 ? fake(js.out1) : nullptr;
             }
@@ -315,7 +329,7 @@ int64_t ld_gemm_program_json(const ld_config* cfg, char* buf, int64_t cap) {
             if (!ld::gemm_build_launch(L, jobs, tune, err)) { fail(LD_ERR_INVALID, "conv " + cs.conv + ": " + err); return -1; }
             if (li) s += ",";
             s += "{\"conv\":\"" + cs.conv + "\",\"cin\":" + std::to_string(L.cin) + ",\"cout\":" + std::to_string(L.cout) +
-                 ",\"w_stack\":" + std::to_string(L.w_stack) + ",\"ext_alloc\":" + std::to_string(L.ext_alloc) +
+                 ",\"w_stack\":" + std::to_string(L.w_stack) + ",\"w_blocks\":" + std::to_string(L.w_blocks) + ",\"ext_alloc\":" + std::to_string(L.ext_alloc) +
                  ",\"groups_per_stage\":" + std::to_string(L.groups_per_stage) + ",\"n_stages\":" + std::to_string(L.n_stages) +
                  ",\"n_rings\":" + std::to_string(L.n_rings) + ",\"n_issuers\":" + std::to_string(L.n_issuers) + ",\"jobs\":[";
             for (int j = 0; j < L.n_jobs; ++j) {
@@ -397,11 +411,11 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         const auto& ps = plan.planes[i];
         PlaneDev& pd = ctx->planes[i];
         const long long guard = static_cast<long long>(ld::kGuardRows) * ps.wp + 256;
-        pd.C = ps.C; pd.wp = ps.wp;
+        pd.C = ps.C * (ps.split ? 2 : 1); pd.wp = ps.wp;   // split precision: [hi | lo] channel chunks
         pd.pixels_alloc = (static_cast<long long>(ctx->rows_alloc) * ps.wp + 2 * guard + 7) & ~7ll;  // chunk stride stays 128 B aligned
         pd.kc_stride = pd.pixels_alloc * 8;
         offs[i] = total;
-        total += static_cast<size_t>(pd.pixels_alloc) * 16 * (ps.C / 8);
+        total += static_cast<size_t>(pd.pixels_alloc) * 16 * (pd.C / 8);
         total = (total + 255) & ~static_cast<size_t>(255);
     }
     ctx->workspace_bytes = total;
@@ -417,11 +431,12 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         if (ctx->weights.count(cs.conv)) continue;
         ConvWeights w;
         w.cin = cs.cin; w.cout = cs.cout; w.ksize = cs.ksize; w.conv = cs.conv; w.bn = cs.bn;
+        w.split_in = cs.split_in != 0; w.split_w = cs.split_w != 0;
         for (const auto& other : plan.convs)
             if (other.conv == cs.conv)
                 for (const auto& js : other.jobs) w.has_res = w.has_res || js.res_plane >= 0;
         if (w.has_res && cs.cin != cs.cout) return cleanup_fail(fail(LD_ERR_INVALID, "residual conv with cin != cout: " + cs.conv));
-        const size_t n = (static_cast<size_t>(cs.ksize) * cs.ksize + (w.has_res ? 1 : 0)) * cs.cin * cs.cout;
+        const size_t n = static_cast<size_t>(w.n_slabs()) * w.cin_eff() * cs.cout;
         LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&w.w), n * sizeof(__half)));
         LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&w.shift), cs.cout * sizeof(float)));
         ctx->weights[cs.conv] = w;
@@ -446,22 +461,31 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         std::memset(&L, 0, sizeof(L));
         const ConvWeights& w = ctx->weights[cs.conv];
         L.weights = w.w; L.shift = w.shift;
-        L.cin = cs.cin; L.cout = cs.cout; L.n_wtaps = cs.ksize * cs.ksize + (w.has_res ? 1 : 0);
+        L.cin = w.cin_eff(); L.cout = cs.cout; L.n_wtaps = w.n_slabs();
         L.relu = cs.relu; L.wp = cs.wp; L.out_mode = cs.out_mode; L.wp2 = cs.wp2; L.hp = cs.hp;
         L.mode = 0;
         L.w_stack = cs.ksize == 3 ? 1 : 0;
+        L.w_blocks = cs.ksize == 3 ? (w.split_w ? 2 : 1) : 0;
+        L.split_out = cs.split_out;
         L.prof = ctx->gemm_prof ? ctx->gemm_prof + 8 * li : nullptr;
         cd.wp = cs.wp;
         std::vector<ld::HostJob> jobs(cs.jobs.size());
         for (size_t j = 0; j < cs.jobs.size(); ++j) {
             const auto& js = cs.jobs[j];
+            const int kk = cs.ksize * cs.ksize;
             std::vector<ld::TapSpec> taps = js.taps;
-            if (js.res_plane >= 0)   // residual add = identity-weight tap on the residual plane (weight slab ksize*ksize)
-                taps.push_back({js.res_plane, js.res_shift, cs.ksize * cs.ksize});
+            if (js.res_plane >= 0)   // residual add = identity-weight tap on the residual plane (the last weight slab)
+                taps.push_back({js.res_plane, js.res_shift, -1});
             for (const auto& t : taps) {
                 const PlaneDev& pd = ctx->planes[t.plane];
-                if (pd.C != cs.cin || pd.wp != cs.wp) return cleanup_fail(fail(LD_ERR_INVALID, "plan/plane mismatch in " + cs.conv));
-                jobs[j].taps.push_back({pd.base, pd.kc_stride, t.shift, t.wtap});
+                if (pd.C != L.cin || pd.wp != cs.wp) return cleanup_fail(fail(LD_ERR_INVALID, "plan/plane mismatch in " + cs.conv));
+                if (t.wtap < 0) {   // identity over the whole [hi | lo] depth: hi and lo of the residual are both added
+                    jobs[j].taps.push_back({pd.base, pd.kc_stride, t.shift, w.n_slabs() - 1, 0});
+                    continue;
+                }
+                // x * w = [x_hi | x_lo] * [w_hi ; w_hi]  +  x_hi * w_lo   (the lo * lo term is below fp32 accumulation noise)
+                jobs[j].taps.push_back({pd.base, pd.kc_stride, t.shift, t.wtap, 0});
+                if (w.split_w) jobs[j].taps.push_back({pd.base, pd.kc_stride, t.shift, kk + t.wtap, w.split_in ? 1 : 0});
             }
             jobs[j].out0 = ctx->planes[js.out0].base;
             jobs[j].out1 = js.out1 >= 0 ? ctx->planes[js.out1].base : nullptr;
@@ -485,6 +509,7 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
     // head
     ctx->head.n_feat = F; ctx->head.C = plan.head_C; ctx->head.groups = plan.head_pool_groups; ctx->head.wp = plan.head_wp;
     ctx->head.params = ctx->head_params;
+    ctx->head.split = plan.planes[plan.head_rows[0].plane].split ? 1 : 0;
     if (plan.head_rows.size() > static_cast<size_t>(ld::kMaxHeadRows)) return cleanup_fail(fail(LD_ERR_INVALID, "too many head rows"));
     for (size_t i = 0; i < plan.head_rows.size(); ++i) {
         ctx->head.rows[i].plane = ctx->planes[plan.head_rows[i].plane].base;
@@ -554,19 +579,30 @@ int ld_resnet_load_weights(ld_ctx* ctx, const ld_tensor* t, int32_t n) {
             return fail(LD_ERR_INVALID, "state_dict is missing or mis-sized: " + cw.conv + ".weight");
         if (b && b->numel != cw.cout) return fail(LD_ERR_INVALID, "mis-sized " + cw.conv + ".bias");
         if (int r = fold_bn(t, n, cw.bn, b ? b->data : nullptr, cw.cout, scale, shift)) return r;
-        // (out, in, kh, kw) fp32 -> [tap][in/8][out][8] fp16: the K-major SWIZZLE_NONE B operand
-        std::vector<__half> packed(static_cast<size_t>(taps + (cw.has_res ? 1 : 0)) * cw.cin * cw.cout, __float2half_rn(0.f));
+        // (out, in, kh, kw) fp32 -> [slab][cin_eff/8][out][8] fp16: the K-major SWIZZLE_NONE B operand.  Slabs: the kh*kw taps
+        // (split precision: then the kh*kw taps of the fp16 rounding residual of the weights), then the identity.
+        // With [hi | lo] input planes the channel chunks cin/8.. multiply the lo half of the activations: hi weights there,
+        // zeros in the lo-weight slabs (never read: those taps run half the K steps).
+        const int cin_eff = cw.cin_eff(), kch = cw.cin / 8;
+        const size_t slab = static_cast<size_t>(cin_eff) * cw.cout;
+        std::vector<__half> packed(static_cast<size_t>(cw.n_slabs()) * slab, __float2half_rn(0.f));
         if (cw.has_res)
-            for (int c = 0; c < cw.cout; ++c)   // identity slab [cin/8][cout][8]
-                packed[((static_cast<size_t>(taps) * (cw.cin / 8) + c / 8) * cw.cout + c) * 8 + (c % 8)] = __float2half_rn(1.f);
+            for (int c = 0; c < cw.cout; ++c)   // identity slab [cin_eff/8][cout][8]: channel c of the hi half and of the lo half
+                for (int part = 0; part < (cw.split_in ? 2 : 1); ++part)
+                    packed[(static_cast<size_t>(cw.n_slabs() - 1) * (cin_eff / 8) + part * kch + c / 8) * cw.cout * 8 +
+                           static_cast<size_t>(c) * 8 + (c % 8)] = __float2half_rn(1.f);
         for (int tap = 0; tap < taps; ++tap)
-            for (int kc = 0; kc < cw.cin / 8; ++kc)
+            for (int kc = 0; kc < kch; ++kc)
                 for (int o = 0; o < cw.cout; ++o)
                     for (int e = 0; e < 8; ++e) {
                         const int i = kc * 8 + e;
                         // BatchNorm scale folded into the fp16 weight: y = conv(x, w * scale) + shift
                         const float v = w->data[(static_cast<size_t>(o) * cw.cin + i) * taps + tap] * scale[o];
-                        packed[((static_cast<size_t>(tap) * (cw.cin / 8) + kc) * cw.cout + o) * 8 + e] = __float2half_rn(v);
+                        const __half hi = __float2half_rn(v);
+                        const size_t at = (static_cast<size_t>(kc) * cw.cout + o) * 8 + e;
+                        packed[tap * slab + at] = hi;
+                        if (cw.split_in) packed[tap * slab + static_cast<size_t>(kch) * cw.cout * 8 + at] = hi;
+                        if (cw.split_w) packed[(taps + tap) * slab + at] = __float2half_rn(v - __half2float(hi));
                     }
         LD_CUDA(cudaMemcpy(cw.w, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
         LD_CUDA(cudaMemcpy(cw.shift, shift.data(), cw.cout * sizeof(float), cudaMemcpyHostToDevice));
@@ -794,12 +830,19 @@ int ld_debug_read_plane(ld_ctx* ctx, int32_t plane_id, int64_t rows, float* out_
     LD_CUDA(cudaSetDevice(ctx->device));
     LD_CUDA(cudaDeviceSynchronize());
     const PlaneDev& p = ctx->planes[plane_id];
+    const bool split = ctx->plan.planes[plane_id].split;
+    const int C = ctx->plan.planes[plane_id].C;   // logical channels; a [hi | lo] plane is returned as hi + lo
     const long long pixels = rows * p.wp;
     std::vector<__half> h(static_cast<size_t>(pixels) * 8);
     for (int kc = 0; kc < p.C / 8; ++kc) {
         LD_CUDA(cudaMemcpy(h.data(), p.base + kc * p.kc_stride, h.size() * sizeof(__half), cudaMemcpyDeviceToHost));
+        const bool lo = split && kc >= C / 8;
+        const int kcl = lo ? kc - C / 8 : kc;
         for (long long px = 0; px < pixels; ++px)
-            for (int e = 0; e < 8; ++e) out_host[px * p.C + kc * 8 + e] = __half2float(h[px * 8 + e]);
+            for (int e = 0; e < 8; ++e) {
+                float& dst = out_host[px * C + kcl * 8 + e];
+                dst = (lo ? dst : 0.f) + __half2float(h[px * 8 + e]);
+            }
     }
     return LD_OK;
 }

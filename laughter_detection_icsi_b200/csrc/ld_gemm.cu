@@ -175,12 +175,13 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
             __syncwarp();
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(L.weights);
             if (L.w_stack) {
-                for (int c = lane; c < 9 * kChunks; c += 32) {
-                    const int slab = c / kChunks, kc = c - slab * kChunks, ky = slab / 3, kx = slab - ky * 3;
-                    bulk_g2s(w_addr + ((kx * kChunks + kc) * 3 + w_stack_row(L.w_stack, ky)) * row_bytes, wsrc + static_cast<size_t>(c) * row_bytes,
-                             row_bytes, bar_w);
+                const int n_stacked = 9 * L.w_blocks;   // split precision: block 0 = hi weights, block 1 = lo weights
+                for (int c = lane; c < n_stacked * kChunks; c += 32) {
+                    const int slab = c / kChunks, kc = c - slab * kChunks, blk = slab / 9, r = slab - blk * 9, ky = r / 3, kx = r - ky * 3;
+                    bulk_g2s(w_addr + blk * 9 * tap_bytes + ((kx * kChunks + kc) * 3 + w_stack_row(L.w_stack, ky)) * row_bytes,
+                             wsrc + static_cast<size_t>(c) * row_bytes, row_bytes, bar_w);
                 }
-                for (int t = 9 + lane; t < n_wtaps; t += 32)
+                for (int t = n_stacked + lane; t < n_wtaps; t += 32)
                     bulk_g2s(w_addr + t * tap_bytes, wsrc + static_cast<size_t>(t) * tap_bytes, tap_bytes, bar_w);
             } else {
                 for (int t = lane; t < n_wtaps; t += 32)
@@ -293,10 +294,11 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
                     const uint32_t b_kstep = w.y >> 15;   // two channel chunks per K = 16: 2 * LBO
                     const uint32_t d = d_tmem + w.z;
                     const uint32_t idesc = idesc0 | w.w;
+                    const int nks = (w.x & kTapHalfK) ? kSteps / 2 : kSteps;   // split precision: hi half of [hi | lo] x lo weights
 #pragma unroll
                     for (int ks = 0; ks < kSteps; ++ks)
                         umma_f16_ss_pred(d, umma_pack_desc(a_lo + ks * a_kstep, desc_hi), umma_pack_desc(b_lo + ks * b_kstep, desc_hi), idesc, 1u,
-                                         mma_on);
+                                         mma_on && ks < nks);
                     if (w.x & kTapLast) {
                         umma_commit_pred(bar_empty + 8 * (ring0 + stage), leader);  // frees the smem stage when these MMAs retire
                         if (profiling) { const long long t1 = clock64(); c_issue += t1 - t0c; t0c = t1; }
@@ -320,6 +322,7 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
         constexpr int CH = COUT / 2;                             // accumulator columns per epilogue warp
         static_assert(CH % 8 == 0, "cout must be a multiple of 16");
         const int wp = L.wp, wp2 = L.wp2, hp = L.hp, relu = L.relu, out_mode = L.out_mode;
+        const bool split_out = MODE == 0 && L.split_out != 0;
         const uint32_t wp_magic = L.wp_magic;
         const int n_acc = L.n_issuers, acc_cols = kTmemCols / n_acc;
         int acc = 0;
@@ -403,6 +406,21 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
                             }
                             if (!inner) ov = make_uint4(0u, 0u, 0u, 0u);
                             *reinterpret_cast<uint4*>(dst + kc * out_kc) = ov;
+                            if (split_out) {   // the fp16 rounding residual goes to channel chunk cout/8 + kc of the [hi | lo] plane
+                                uint4 lv;
+                                __half2* lh = reinterpret_cast<__half2*>(&lv);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int c = kc * 8 + 2 * e;
+                                    float a = __uint_as_float(v[c]) + sh[2 * e];
+                                    float b = __uint_as_float(v[c + 1]) + sh[2 * e + 1];
+                                    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                                    const float2 hi = __half22float2(oh[e]);
+                                    lh[e] = __floats2half2_rn(a - hi.x, b - hi.y);
+                                }
+                                if (!inner) lv = make_uint4(0u, 0u, 0u, 0u);
+                                *reinterpret_cast<uint4*>(dst + (COUT / 8 + kc) * out_kc) = lv;
+                            }
                         }
                     }
                 } else {

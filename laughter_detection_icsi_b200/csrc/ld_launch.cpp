@@ -32,6 +32,7 @@ struct Tap {          // one (input operand, weight slab) product feeding output
     long long kc_stride;
     int shift, wslab, out;
     int group, off;   // load group inside the job, pixel offset inside the group
+    int half_k;
 };
 
 bool shares_input(const HostJob& a, const HostJob& b) {
@@ -53,7 +54,9 @@ bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
         const char* p = std::getenv("LD_GEMM_PROF");
         L.dbg = (v && p && std::atoi(p)) ? std::atoi(v) : 0;
     }
-    if (L.w_stack && L.n_wtaps < 9) { err = "stacked weights need a 3x3 kernel"; return false; }
+    if (L.w_stack && L.w_blocks < 1) L.w_blocks = 1;
+    if (!L.w_stack) L.w_blocks = 0;
+    if (L.w_stack && L.n_wtaps < 9 * L.w_blocks) { err = "stacked weights need a 3x3 kernel"; return false; }
     // cout >= 48: two issuers with 256 accumulator columns each (chains of up to 4 outputs); narrower layers are bound by
     // the issue latency of their small MMAs: four issuers with 128 columns each
     L.n_issuers = L.cout >= 48 ? tune.issuers_wide : tune.issuers_narrow;
@@ -109,7 +112,7 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
         std::vector<Tap>& taps = job_taps[j];
         for (int o = parts[j].first; o < parts[j].second; ++o) {
             if (outs[o].taps.empty()) { err = "output without taps"; return false; }
-            for (const auto& t : outs[o].taps) taps.push_back({t.src, t.kc_stride, t.shift, t.wslab, o - parts[j].first, -1, 0});
+            for (const auto& t : outs[o].taps) taps.push_back({t.src, t.kc_stride, t.shift, t.wslab, o - parts[j].first, -1, 0, t.half_k});
             job.outs[o - parts[j].first] = {static_cast<__half*>(outs[o].out0), static_cast<__half*>(outs[o].out1)};
             if (outs[o].out_kc_stride != outs[parts[j].first].out_kc_stride) { err = "outputs of a job differ in layout"; return false; }
         }
@@ -126,8 +129,9 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
             Group& g = groups.back();
             g.ext = std::max(g.ext, kTileM + t.shift - g.g_min);
             // chain position of the operand: input row = output row + ky - 1 (identity / 1x1 taps sit at their output)
-            const int ky = (stack && t.wslab < 9) ? t.wslab / 3 : 1;
-            g.order = std::min(g.order, 4 * (t.out + ky - 1) + ((stack && t.wslab >= 9) ? 1 : 0));
+            const int n_stacked = 9 * L.w_blocks;
+            const int ky = (stack && t.wslab < n_stacked) ? (t.wslab % 9) / 3 : 1;
+            g.order = std::min(g.order, 4 * (t.out + ky - 1) + ((stack && t.wslab >= n_stacked) ? 1 : 0));
             t.group = static_cast<int>(groups.size()) - 1;
             t.off = t.shift - g.g_min;
         }
@@ -169,8 +173,10 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
         std::vector<Tap>& taps = job_taps[j];
         uint4* tapw = L.taps + n_launch_taps;
         // weight row block of a tap inside its stacked block (ky = 2, 1, 0 or ky = 2, 0, 1), or -1 for a stand-alone slab
-        auto wrow = [&](const Tap& t) { return (stack && t.wslab < 9) ? w_stack_row(L.w_stack, t.wslab / 3) : -1; };
-        auto kx_of = [&](const Tap& t) { return (stack && t.wslab < 9) ? t.wslab % 3 : t.wslab; };
+        const int n_stacked = 9 * L.w_blocks;
+        auto wrow = [&](const Tap& t) { return (stack && t.wslab < n_stacked) ? w_stack_row(L.w_stack, (t.wslab % 9) / 3) : -1; };
+        // merge key: column kx of weight block b (taps of different blocks never merge); stand-alone slabs keep their index
+        auto kx_of = [&](const Tap& t) { return (stack && t.wslab < n_stacked) ? (t.wslab / 9) * 3 + t.wslab % 3 : 64 + t.wslab; };
         std::sort(taps.begin(), taps.end(), [&](const Tap& a, const Tap& b) {
             return std::make_tuple(a.group, a.off, kx_of(a), a.out) < std::make_tuple(b.group, b.off, kx_of(b), b.out);
         });
@@ -180,7 +186,8 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
             size_t e = i + 1;
             if (wrow(taps[i]) >= 0)
                 while (e < taps.size() && taps[e].group == taps[i].group && taps[e].off == taps[i].off &&
-                       kx_of(taps[e]) == kx_of(taps[i]) && wrow(taps[e]) >= 0 && taps[e].out == taps[e - 1].out + 1 &&
+                       kx_of(taps[e]) == kx_of(taps[i]) && wrow(taps[e]) >= 0 && taps[e].half_k == taps[i].half_k &&
+                       taps[e].out == taps[e - 1].out + 1 &&
                        wrow(taps[e]) == wrow(taps[e - 1]) + 1)
                     ++e;
             if (n >= kMaxTaps || n_launch_taps + n >= kMaxLaunchTaps) { err = "too many MMA taps in a job"; return false; }
@@ -189,7 +196,8 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
             const uint32_t a16 = static_cast<uint32_t>(t.group % gps) * box16 + static_cast<uint32_t>(t.off);
             uint32_t b16, lbo16;
             if (wrow(t) >= 0) {
-                b16 = static_cast<uint32_t>(kx_of(t)) * kchunks * 3u * L.cout + static_cast<uint32_t>(wrow(t)) * L.cout;
+                const uint32_t blk = static_cast<uint32_t>(t.wslab / 9), kx = static_cast<uint32_t>(t.wslab % 3);
+                b16 = blk * 9u * kchunks * L.cout + kx * kchunks * 3u * L.cout + static_cast<uint32_t>(wrow(t)) * L.cout;
                 lbo16 = 3u * L.cout;
             } else {
                 b16 = static_cast<uint32_t>(t.wslab) * kchunks * L.cout;
@@ -201,7 +209,7 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
             const bool last = e == taps.size() || taps[e].group / gps != stage_of;
             const uint32_t col = static_cast<uint32_t>(t.out) * L.cout, ncols = static_cast<uint32_t>(n_merged) * L.cout;
             if (col + ncols > static_cast<uint32_t>(kTmemCols / L.n_issuers)) { err = "accumulator overflow"; return false; }
-            tapw[n].x = a16 | (first ? kTapFirst : 0u) | (last ? kTapLast : 0u);
+            tapw[n].x = a16 | (first ? kTapFirst : 0u) | (last ? kTapLast : 0u) | (t.half_k ? kTapHalfK : 0u);
             tapw[n].y = b16 | (lbo16 << 16);
             tapw[n].z = col;
             tapw[n].w = (ncols >> 3) << 17;

@@ -128,14 +128,16 @@ head_kernel(HeadLaunch L, ChannelTable ct, float* __restrict__ probs, long long 
         const int g = i >> 2;
         for (int kc = 0; kc < C / 8; ++kc) {
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int part = 0; part <= L.split; ++part) {   // [hi | lo] planes: the rounding residual sits C/8 chunks further
 #pragma unroll
-            for (int cpx = 0; cpx < 4; ++cpx) {
-                const uint4 v = *reinterpret_cast<const uint4*>(base + kc * hr.kc_stride + cpx * 8);
-                const __half2* vh = reinterpret_cast<const __half2*>(&v);
+                for (int cpx = 0; cpx < 4; ++cpx) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(base + (kc + part * (C / 8)) * hr.kc_stride + cpx * 8);
+                    const __half2* vh = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 f = __half22float2(vh[e]);
-                    acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __half22float2(vh[e]);
+                        acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+                    }
                 }
             }
 #pragma unroll

@@ -47,6 +47,7 @@ struct HeadLaunch {
     HeadRow rows[kMaxHeadRows];
     const float* params;  // bn2 scale/shift, linear1, bn3 scale/shift, linear2 (see ld_net.cu)
     int n_feat, C, groups, wp;
+    int split;            // the planes are [hi | lo]: chunks C/8.. hold the fp16 rounding residual, added back in fp32
 };
 
 cudaError_t launch_stem(const StemLaunch& L, const ChannelTable& ct, const float* feats, long long chunk_row0,
@@ -64,7 +65,9 @@ struct HostTap {
     const void* src;      // pixel 0, chunk 0 of the source plane
     long long kc_stride;  // elements between its channel chunks
     int shift;            // pixel shift of the tap
-    int wslab;            // weight slab index (3x3: ky * 3 + kx; 9: the identity / shortcut slab)
+    int wslab;            // weight slab index: 3x3 block b (0 = hi, 1 = lo weights): 9 * b + ky * 3 + kx; slabs after the
+                          // blocks (identity / 1x1 weights) are stand-alone
+    int half_k = 0;       // split precision: multiply only the first half of the channel chunks (the hi half of [hi | lo])
 };
 struct HostJob {   // one OUTPUT plane; gemm_build_launch packs chains of them into GemmJobs
     std::vector<HostTap> taps;

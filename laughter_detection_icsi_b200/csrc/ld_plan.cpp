@@ -21,6 +21,7 @@ namespace {
 struct Level {
     int H = 0, W = 0, C = 0, res = 1;
     bool colsplit = false;   // stored as even/odd column planes in the consumer's geometry
+    bool split = false;      // split precision: [hi | lo] planes
     int wp = 0;              // padded width of the stored planes
     std::set<int> spec;      // window-specific local rows
     std::set<int> needed;    // local rows some consumer reads
@@ -73,15 +74,19 @@ Plan build_stream_plan(const NetConfig& cfg) {
                 lv[cur].colsplit = true;
                 lv[cur].wp = Wo + 2;
             }
+            const bool split = cfg.precision == 1 && b >= 1;   // blocks 2-4 (tools/precision_budget.py: block1 does not need it)
             const int h = new_level(Ho, Wo, out_c, x.res * s, pre + ".h");
+            lv[h].split = split;
             ops.push_back({pre + ".conv1", pre + ".bn1", cur, h, -1, s, 3, 1});
             int res_level = cur;
             if (s != 1 || ic != out_c) {
                 const int sc = new_level(Ho, Wo, out_c, x.res * s, pre + ".sc");
+                lv[sc].split = split;
                 ops.push_back({pre + ".shortcut.0", pre + ".shortcut.1", cur, sc, -1, s, 1, 0});
                 res_level = sc;
             }
             const int y = new_level(Ho, Wo, out_c, x.res * s, pre + ".y");
+            lv[y].split = split;
             ops.push_back({pre + ".conv2", pre + ".bn2", h, y, res_level, 1, 3, 1});
             cur = y;
         }
@@ -149,15 +154,17 @@ Plan build_stream_plan(const NetConfig& cfg) {
     }
 
     // ---- planes ------------------------------------------------------------------------------------
+    bool cur_split = false;
     auto new_plane = [&](int C, int wp, const std::string& tag) {
         PlaneSpec p;
         p.id = static_cast<int>(plan.planes.size());
-        p.C = C; p.wp = wp; p.tag = tag;
+        p.C = C; p.wp = wp; p.tag = tag; p.split = cur_split;
         plan.planes.push_back(p);
         return p.id;
     };
     for (auto& l : lv) {
         bool any_interior = false;
+        cur_split = l.split;
         for (int i : l.needed) {
             if (l.spec.count(i)) {
                 l.spec_plane[i] = new_plane(l.C, l.wp, l.tag + ".r" + std::to_string(i) + (l.colsplit ? ".e" : ""));
@@ -208,6 +215,8 @@ Plan build_stream_plan(const NetConfig& cfg) {
         L.out_mode = out.colsplit ? OUT_COLSPLIT : OUT_PLAIN;
         L.wp2 = out.wp;
         L.hp = 0;
+        L.split_in = in.split; L.split_out = out.split; L.split_w = out.split;
+        if (op.res >= 0 && lv[op.res].split != in.split) throw std::runtime_error("planner: residual/input precision mismatch at " + op.conv);
         if ((op.stride == 1 && (in.colsplit || in.wp != L.wp)) ||
             (op.stride == 2 && (!in.colsplit || in.wp != L.wp)))
             throw std::runtime_error("planner: storage geometry mismatch at " + op.conv);
@@ -265,7 +274,8 @@ Plan build_stream_plan(const NetConfig& cfg) {
             L.jobs.push_back(job);
         }
         for (auto& job : L.jobs) {
-            const double m = static_cast<double>(job.taps.size()) * L.cin * L.cout * L.wp;
+            // split precision executes hi*hi + lo*hi + hi*lo (three products per tap; two when the input is plain fp16)
+            const double m = static_cast<double>(job.taps.size()) * L.cin * L.cout * L.wp * (L.split_w ? (L.split_in ? 3 : 2) : 1);
             plan.macs_per_row += m;
             plan.gemm_macs_per_row += m;
         }
@@ -296,7 +306,8 @@ std::string plan_to_json(const Plan& plan) {
       << ",\"macs_per_row\":" << static_cast<long long>(plan.macs_per_row) << ",\"planes\":[";
     for (size_t i = 0; i < plan.planes.size(); ++i) {
         const auto& p = plan.planes[i];
-        o << (i ? "," : "") << "{\"id\":" << p.id << ",\"C\":" << p.C << ",\"wp\":" << p.wp << ",\"tag\":\"" << p.tag << "\"}";
+        o << (i ? "," : "") << "{\"id\":" << p.id << ",\"C\":" << p.C << ",\"wp\":" << p.wp << ",\"split\":" << (p.split ? 1 : 0)
+          << ",\"tag\":\"" << p.tag << "\"}";
     }
     o << "],\"stem_wp\":" << plan.stem_wp << ",\"stem\":[";
     for (size_t i = 0; i < plan.stem.size(); ++i) {
@@ -308,7 +319,8 @@ std::string plan_to_json(const Plan& plan) {
         const auto& c = plan.convs[i];
         o << (i ? "," : "") << "{\"conv\":\"" << c.conv << "\",\"bn\":\"" << c.bn << "\",\"cin\":" << c.cin
           << ",\"cout\":" << c.cout << ",\"ksize\":" << c.ksize << ",\"relu\":" << c.relu << ",\"wp\":" << c.wp
-          << ",\"out_mode\":" << c.out_mode << ",\"wp2\":" << c.wp2 << ",\"hp\":" << c.hp << ",\"jobs\":[";
+          << ",\"out_mode\":" << c.out_mode << ",\"wp2\":" << c.wp2 << ",\"hp\":" << c.hp << ",\"split_in\":" << c.split_in
+          << ",\"split_out\":" << c.split_out << ",\"split_w\":" << c.split_w << ",\"jobs\":[";
         for (size_t j = 0; j < c.jobs.size(); ++j) {
             const auto& job = c.jobs[j];
             o << (j ? "," : "") << "{\"tag\":\"" << job.tag << "\",\"out0\":" << job.out0 << ",\"out1\":" << job.out1

@@ -21,8 +21,8 @@ namespace ld {
 
 constexpr int kTileM = 128;      // output pixels per MMA tile (UMMA M)
 constexpr int kMaxGroups = 16;   // distinct smem loads per job
-constexpr int kMaxTaps = 32;     // MMA taps per job
-constexpr int kMaxLaunchTaps = 192;  // MMA taps per launch (all jobs; 16 unmerged 3x3 outputs + residuals = 160)
+constexpr int kMaxTaps = 64;     // MMA taps per job (split precision doubles the taps of a job: hi and lo weight blocks)
+constexpr int kMaxLaunchTaps = 384;  // MMA taps per launch (all jobs); the table travels as a kernel parameter (6 KB of the 32 KB)
 constexpr int kMaxOuts = 8;      // output planes per job (their accumulators sit side by side in TMEM)
 constexpr int kTmemCols = 512;   // accumulator columns per SM, split into n_issuers stages: n_outs * cout <= 512 / n_issuers
 constexpr int kMaxJobs = 16;     // jobs per launch (the planner also splits a layer into launches of at most this many output planes)
@@ -64,7 +64,8 @@ struct GemmGroup {
 //   y: low word of the B smem descriptor relative to the weights: bits 0..13 offset of the weight rows, bits 16..29 LBO
 //      (rows per channel chunk: 3 * cout inside a stacked block, cout for a stand-alone slab [cin/8][cout][8])
 //   z: first accumulator column                w: N / 8 << 17 (the N field of the instruction descriptor)
-constexpr uint32_t kTapFirst = 1u << 28, kTapLast = 1u << 29, kTapPass = 1u << 30;
+//      bit 27 half K: only the first cin/32 K steps (split precision: the hi half of a [hi | lo] activation against lo weights)
+constexpr uint32_t kTapFirst = 1u << 28, kTapLast = 1u << 29, kTapPass = 1u << 30, kTapHalfK = 1u << 27;
 struct GemmOut {
     __half* out0;  // PLAIN: the plane; COLSPLIT: even-column plane
     __half* out1;  // COLSPLIT: odd-column plane
@@ -100,7 +101,10 @@ struct GemmParams {         // the kernel's __grid_constant__ parameter
     int32_t groups_per_stage;  // consecutive groups of a job that share one smem stage (one barrier round trip)
     uint32_t wp_magic;  // floor(2^32 / wp) + 1: row = umulhi(pixel, wp_magic)
     int32_t w_stack;    // 1, 2: 3x3 weights are re-stacked in smem as [kx][cin/8][ky order][cout][8], order ky = 2,1,0 (1) or
-                        // 2,0,1 (2, stride-2 convs), see w_stack_row; slab 9, if any, stays a slab.  0: plain slabs
+                        // 2,0,1 (2, stride-2 convs), see w_stack_row; slabs from 9 * w_blocks on stay slabs.  0: plain slabs
+    int32_t w_blocks;   // stacked 3x3 blocks at the head of the weights: 1, or 2 in split precision (hi weights, lo weights)
+    int32_t split_out;  // split precision: the epilogue also writes the fp16 rounding residual as channel chunks cout/8.. of the
+                        // output plane ([hi | lo] planes)
     int32_t dbg;        // timing experiments only (LD_GEMM_DBG, results are garbage): bit 0 one copy per smem stage, bit 1 no MMAs,
                         // bit 2 no global stores, bit 3 no TMEM reads/clears in the epilogue
     int32_t n_issuers;  // MMA-issuing warps = accumulator stages (2: 256 columns each, 4: 128 columns each)
@@ -118,6 +122,7 @@ struct GemmLaunch : GemmParams {   // host side: the parameters plus the job tab
 struct PlaneSpec {
     int id;
     int C;       // channels (multiple of 8)
+    bool split = false;  // split precision: stored as [hi | lo] = 2 * C channel chunks
     int wp;      // padded width
     std::string tag;
 };
@@ -136,6 +141,7 @@ struct ConvLaunchSpec {
     std::string conv;  // state_dict prefix of the conv, e.g. "block2.0.conv1"
     std::string bn;    // state_dict prefix of the BatchNorm that follows
     int cin, cout, ksize, relu, wp, out_mode, wp2, hp;
+    int split_in = 0, split_out = 0, split_w = 0;   // split precision: [hi | lo] input planes / output planes / hi + lo weights
     std::vector<JobSpec> jobs;
 };
 struct StemJobSpec {
@@ -164,6 +170,7 @@ struct NetConfig {
     int H = 100, W = 44;
     int filters[4] = {64, 32, 16, 16};
     int linear_in = 48;
+    int precision = 0;   // ld_precision: 1 = blocks 2-4 carry weights and activations as hi + lo fp16 pairs
 };
 
 Plan build_stream_plan(const NetConfig& cfg);

@@ -25,8 +25,13 @@ class PlanEmulator:
         self.half = half
         self.planes = {}
 
-    def _q(self, x):
-        return x.half().float() if self.half else x
+    def _q(self, x, split=False):
+        """fp16 rounding where the kernels round; split=True keeps the rounding residual as a second fp16 value (hi + lo),
+        what precision='split' stores for the weights and planes of blocks 2-4."""
+        if not self.half:
+            return x
+        hi = x.half().float()
+        return hi + (x - hi).half().float() if split else hi
 
     def run(self, feats, nb):
         """feats: (T, W) float tensor of ONE channel starting at sequence row 0; evaluates window starts
@@ -76,7 +81,7 @@ class PlanEmulator:
             bias = self.sd.get(c["conv"] + ".bias")
             s, sh = fold_bn(self.sd, c["bn"], bias)
             k = c["ksize"]
-            wtaps = self._q(wt.reshape(c["cout"], c["cin"], k * k) * s[:, None, None])  # BN scale folded into fp16 weights
+            wtaps = self._q(wt.reshape(c["cout"], c["cin"], k * k) * s[:, None, None], c.get("split_w", 0))  # BN scale folded into fp16 weights
             wp = c["wp"]
             M = rows * wp
             col = torch.arange(M) % wp
@@ -94,7 +99,7 @@ class PlanEmulator:
                     y = y + self.planes[job["res"]][g + job["res_shift"]:g + job["res_shift"] + M]
                 if c["relu"]:
                     y = torch.relu(y)
-                y = self._q(y * inner[:, None])
+                y = self._q(y * inner[:, None], c.get("split_out", 0))
                 if c["out_mode"] == 0:
                     g = self.geom[job["out0"]][1]
                     self.planes[job["out0"]][g:g + M] = y

@@ -190,6 +190,52 @@ def test_calibrated_head_checkpoint_error_budget(engine):
     assert np.abs(logit(probs[ok].astype(np.float64)) - logit(ref[ok])).max() / synth.HEAD_GAIN < 1e-3
 
 
+def test_split_precision_meets_2e3_on_the_calibrated_checkpoint():
+    """precision='split' (ld_config.precision = LD_PRECISION_SPLIT): blocks 2-4 carry weights and stored
+    activations as hi + lo fp16 pairs.  On the bench checkpoint (head gain ~218) the probabilities are within 2e-3 of the fp64
+    oracle (plain fp16: ~5e-3 .. 1e-2), incl. ragged channels and the zero-padded tail windows; every stored plane agrees
+    with the CPU emulation of the same rounding model."""
+    from plan_emulator import PlanEmulator
+    eng = Engine(0, chunk_rows=1024, precision="split")
+    try:
+        sd = synth.synthetic_state_dict()
+        eng.load_state_dict(sd)
+        chans = [synth.synth_channel(16000 * 7 + 11, meeting=3, channel=0), synth.synth_channel(16000 * 2 + 5, meeting=3, channel=1)]
+        lens = [c.numel() for c in chans]
+        feats, frames = eng.fbank(torch.cat(chans).cuda(), lens)
+        probs = eng.infer_windows(feats, frames).cpu().numpy()
+        f = feats.cpu().numpy()
+        off = 0
+        worst = 0.0
+        for t in frames:
+            ref = resnet_oracle.window_probs(sd, f[off:off + t], dtype=torch.float64)
+            worst = max(worst, float(np.abs(probs[off:off + t] - ref).max()))
+            off += t
+        print(f"split precision: max |dp| = {worst:.2e} over {sum(frames)} windows")
+        assert worst < 2e-3
+        # plane-level: one channel of 150 frames against the emulator with the same rounding (hi + lo where the plan says so)
+        plan = _native.plan_json(eng.cfg)
+        nb = 150
+        one = torch.from_numpy(f[:nb]).cuda().contiguous()
+        p_gpu = eng.infer_windows(one, [nb]).cpu().numpy()
+        emu = PlanEmulator(plan, sd, half=True)
+        p_emu = emu.run(torch.from_numpy(f[:nb]), nb).numpy()
+        assert np.abs(p_gpu - p_emu).max() < 2e-4   # same rounding model; fp32 summation order differs
+        for tag in ("block2.0.h.int", "block2.1.y.int.e", "block3.1.y.r0.e", "block4.1.y.r5"):
+            pl = next(p for p in plan["planes"] if p["tag"] == tag)
+            got = eng.read_plane(pl["id"], nb + 100, pl["wp"], pl["C"])
+            want = emu.plane_as_rows(pl["id"], nb + 100).numpy()
+            scale = np.abs(want).max()
+            assert np.abs(got - want).max() < 2e-4 * scale, tag
+        # random-init weights: far inside the 1e-3 of the north star
+        sd2 = resnet_oracle.random_state_dict(seed=3)
+        eng.load_state_dict(sd2)
+        p2 = eng.infer_windows(one, [nb]).cpu().numpy()
+        assert np.abs(p2 - resnet_oracle.window_probs(sd2, f[:nb], dtype=torch.float64)).max() < 1e-4
+    finally:
+        eng.close()
+
+
 def test_unloaded_weights_and_bad_shapes_fail_loudly():
     eng = Engine(0, chunk_rows=256)
     try:

@@ -65,13 +65,14 @@ def _expand_tap_program(conv):
     products, checking the stage bookkeeping flags on the way."""
     cin, cout, gps = conv["cin"], conv["cout"], conv["groups_per_stage"]
     kchunks, box16 = cin // 8, conv["ext_alloc"] * (cin // 8)
+    n_stacked = 9 * conv["w_blocks"]
     products = []
     for job in conv["jobs"]:
         stage, n_first, n_last, n_pass, open_stage = -1, 0, 0, 0, False
         assert len(job["outs"]) * cout <= 512 // conv["n_issuers"]
         for x, y, z, w in job["taps"]:
             a16, b16, lbo16 = x & 0x3FFF, y & 0x3FFF, (y >> 16) & 0x3FFF
-            first, last, passing = bool(x & (1 << 28)), bool(x & (1 << 29)), bool(x & (1 << 30))
+            first, last, passing, half_k = bool(x & (1 << 28)), bool(x & (1 << 29)), bool(x & (1 << 30)), int(bool(x & (1 << 27)))
             slab = lbo16 == cout
             assert lbo16 in (cout, 3 * cout) and y >> 30 == 0
             if first:
@@ -92,13 +93,15 @@ def _expand_tap_program(conv):
                 if slab:
                     assert n == cout and b16 % (kchunks * cout) == 0
                     wtap = b16 // (kchunks * cout)
+                    assert wtap >= n_stacked
                 else:
                     assert conv["w_stack"] in (1, 2)
-                    kx, rem = divmod(b16, kchunks * 3 * cout)
-                    assert rem % cout == 0 and rem // cout + n // cout <= 3
+                    blk, in_blk = divmod(b16, 9 * kchunks * cout)    # split precision: block 0 = hi weights, block 1 = lo weights
+                    kx, rem = divmod(in_blk, kchunks * 3 * cout)
+                    assert blk < conv["w_blocks"] and rem % cout == 0 and rem // cout + n // cout <= 3
                     ky = {1: (2, 1, 0), 2: (2, 0, 1)}[conv["w_stack"]][rem // cout + i]   # stacking order of the weight rows
-                    wtap = ky * 3 + kx
-                products.append((job["outs"][col // cout + i][0], src, gshift + off, wtap))
+                    wtap = blk * 9 + ky * 3 + kx
+                products.append((job["outs"][col // cout + i][0], src, gshift + off, wtap, half_k))
             if last:
                 n_last += 1; open_stage = False
         assert not open_stage and n_first == n_last == job["n_stages"] == -(-len(job["groups"]) // gps) and n_pass == 1
@@ -106,21 +109,27 @@ def _expand_tap_program(conv):
     return products
 
 
-@pytest.mark.parametrize("filters", [(64, 32, 16, 16), (64, 48, 32, 16), (64, 64, 32, 16), (64, 16, 16, 16)])
-def test_tap_program_covers_the_plan(filters):
+@pytest.mark.parametrize("filters,precision", [((64, 32, 16, 16), 0), ((64, 48, 32, 16), 0), ((64, 64, 32, 16), 0), ((64, 16, 16, 16), 0),
+                                               ((64, 32, 16, 16), 1), ((64, 32, 32, 16), 1)])
+def test_tap_program_covers_the_plan(filters, precision):
     """The N-stacked tap programs (chains of outputs, merged MMAs) multiply exactly the products the plan lists -- for
-    resnet_base and for other channel widths the kernels are instantiated for."""
-    cfg = _native.default_config(filter_sizes=filters)
+    resnet_base and for other channel widths the kernels are instantiated for; with precision=split (1) every product of
+    blocks 2-4 appears against the hi weights (full [hi | lo] depth) and against the lo weights (hi half only)."""
+    cfg = _native.default_config(filter_sizes=filters, precision=precision)
     plan = _native.plan_json(cfg)
     prog = _native.gemm_program_json(cfg)
     assert [c["conv"] for c in prog["convs"]] == [c["conv"] for c in plan["convs"]]
     merged = 0
     for pc, gc in zip(plan["convs"], prog["convs"]):
         want = []
+        kk = pc["ksize"] ** 2
         for job in pc["jobs"]:
-            want += [(job["out0"], p, s, t) for p, s, t in job["taps"]]
+            want += [(job["out0"], p, s, t, 0) for p, s, t in job["taps"]]
+            if pc["split_w"]:
+                want += [(job["out0"], p, s, kk + t, pc["split_in"]) for p, s, t in job["taps"]]
             if job["res"] >= 0:
-                want.append((job["out0"], job["res"], job.get("res_shift", 0), pc["ksize"] ** 2))
+                want.append((job["out0"], job["res"], job.get("res_shift", 0), kk * (2 if pc["split_w"] else 1), 0))
+        assert gc["cin"] == pc["cin"] * (2 if pc["split_in"] else 1)
         got = _expand_tap_program(gc)
         assert sorted(got) == sorted(want), gc["conv"]
         assert [tuple(o) for j in gc["jobs"] for o in j["outs"]] == [(j["out0"], j["out1"]) for j in pc["jobs"]]
@@ -129,9 +138,36 @@ def test_tap_program_covers_the_plan(filters):
     assert merged > 300, "chains of window-specific rows share their input loads and MMAs"
 
 
+def test_split_precision_plan_and_error_budget():
+    """precision='split' (DESIGN.md section 7): blocks 2-4 keep weights and stored activations as hi + lo fp16 pairs.  On the
+    calibrated-head bench checkpoint (head gain ~218) the emulated rounding model stays within 2e-3 of the fp64 oracle where
+    plain fp16 is at ~5e-3; block1 stays plain fp16 (tools/precision_budget.py: splitting it buys nothing)."""
+    from laughter_detection_icsi_b200 import synth
+    from oracle import fbank_oracle
+    cfg = _native.default_config(precision=1)
+    plan = _native.plan_json(cfg)
+    split = {p["tag"].split(".")[0] for p in plan["planes"] if p["split"]}
+    plain = {p["tag"].split(".")[0] for p in plan["planes"] if not p["split"]}
+    assert split == {"block2", "block3", "block4"} and plain == {"stem", "block1"}
+    for c in plan["convs"]:
+        assert c["split_w"] == c["split_out"] == int(not c["conv"].startswith("block1"))
+        assert c["split_in"] == int(c["conv"].startswith(("block3", "block4", "block2.1")) or c["conv"] == "block2.0.conv2")
+    # blocks 2-4 are 12.4 of the 62.4 MMAC: three (two for block2.0's fp16 input) products per tap
+    assert 62.4e6 < plan["macs_per_row"] < 62.4e6 + 2.0 * 12.5e6
+    assert _native.plan_plane_bytes_per_row(cfg) > _native.plan_plane_bytes_per_row() + 200e3
+    sd = synth.synthetic_state_dict()
+    nb = 48
+    pcm = synth.synth_channel(nb * 160 + 16000 + 37, meeting=0, channel=0)
+    feats = fbank_oracle.fbank(pcm.numpy().astype(np.float32) / 32768.0)[: nb + 100]
+    ref = resnet_oracle.window_probs(sd, feats.numpy(), dtype=torch.float64)[:nb]
+    err_split = np.abs(PlanEmulator(plan, sd, half=True).run(feats, nb).double().numpy() - ref).max()
+    err_fp16 = np.abs(PlanEmulator(_native.plan_json(), sd, half=True).run(feats, nb).double().numpy() - ref).max()
+    assert err_split < 2e-3 and err_split < err_fp16
+
+
 def test_plane_traffic_per_row():
-    """The algorithmic HBM traffic of the conv stack behind bench.py's roofline: ~733 KB of fp16 planes per frame, i.e. 85 FLOP
-    per byte with the 62.4 MMAC the plan executes -- left of the B200 ridge, the stack is HBM-bound."""
+    """The algorithmic HBM traffic of the conv stack behind bench.py's roofline: ~733 KB of fp16 planes per frame, i.e. 85 MAC =
+    170 FLOP per byte with the 62.4 MMAC the plan executes -- just left of the B200 ridge (~215 FLOP/B)."""
     b = _native.plan_plane_bytes_per_row()
     assert b == 732928.0
     plan = _native.plan_json()
