@@ -10,6 +10,7 @@
 // pre-processed span of 15*160+400 samples.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "ld_net.h"
@@ -62,141 +63,217 @@ __device__ __forceinline__ void dft16(float2 (&a)[16]) {
         }
 }
 
+constexpr int kSpanPad = kSpan + 16;    // pass 1 reads 416 samples per frame (the window is zero past 400)
+constexpr int kWinPad = kFrameLen + 16;
+constexpr int kTrFloats = 2 * 16 * 17;   // floats of one frame's transpose buffer (16 x 17 complex)
+constexpr int kStageOff = 264;           // floats: the frame's 44 log-mel outputs wait here (behind its 257 power values)
+
 struct FbankSmem {
-    float samples[kSpan];                      // pre-processed (utterance mode) or raw (frame mode) samples
-    float window[kFrameLen];
-    float2 tw256[kFftHalf];
+    float samples[kSpanPad];                   // pre-processed (utterance mode) or raw (frame mode) samples
+    float window[kWinPad];                     // Povey window, zero-padded to 416
     float2 tw512[kBins];
-    float2 tr[kFramesPerCta][16 * 17];          // per frame: transpose buffer, then the FFT output Z
-    float pw[kFramesPerCta][kBins + 3];         // per frame: power spectrum
+    float tr[kFramesPerCta][kTrFloats];        // per frame: transpose buffer between the two radix-16 passes, then the power
+                                               // spectrum (257 floats) and the staged outputs (aliased: the passes are done)
     float melw[kMaxMelWeights];
     int mel_lo[kMaxFilters], mel_len[kMaxFilters], mel_off[kMaxFilters];
 };
 
-template <bool kPerFrame>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ float pcm_to_float(int v) { return static_cast<float>(v) * (1.f / 32768.f); }
+
+// kMinBlocks: CTAs per SM the register allocation aims for (2: 128 registers, 3: 80, 4: 64 with 68 bytes of spills)
+template <bool kPerFrame, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
 fbank_kernel(const int16_t* __restrict__ pcm, long long n_samples, long long n_frames,
              const unsigned long long* __restrict__ sum_biased, FbankMel mel, const float* __restrict__ tables,
              float* __restrict__ feats) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     FbankSmem& S = *reinterpret_cast<FbankSmem*>(smem_raw);
     const int tid = threadIdx.x;
+    const int fl = tid >> 4;  // frame within the group
+    const int t = tid & 15;   // thread within the frame
+    const unsigned gmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
+    const int lane_base = threadIdx.x & 16;   // first lane of this frame's 16 threads inside the warp
 
-    // ---- stage tables and this CTA's sample span ------------------------------------------------------
-    for (int i = tid; i < kFrameLen; i += 256) S.window[i] = tables[i];
-    for (int i = tid; i < kFftHalf; i += 256) S.tw256[i] = make_float2(tables[400 + 2 * i], tables[400 + 2 * i + 1]);
+    // ---- tables: once per CTA (128 frames) --------------------------------------------------------------
+    for (int i = tid; i < kWinPad; i += 256) S.window[i] = i < kFrameLen ? tables[i] : 0.f;
     for (int i = tid; i < kBins; i += 256) S.tw512[i] = make_float2(tables[912 + 2 * i], tables[912 + 2 * i + 1]);
+    for (int i = kSpan + tid; i < kSpanPad; i += 256) S.samples[i] = 0.f;
     const int F = mel.n_filters;
     for (int i = tid; i < F; i += 256) { S.mel_lo[i] = mel.lo[i]; S.mel_len[i] = mel.len[i]; S.mel_off[i] = mel.off[i]; }
     {
         const int total_w = mel.off[F - 1] + mel.len[F - 1];
         for (int i = tid; i < total_w; i += 256) S.melw[i] = mel.weights[i];
     }
-    // the tables are staged once per CTA; the CTA then walks kGroupsPerCta consecutive groups of 16 frames
-    for (int grp = 0; grp < kGroupsPerCta; ++grp) {
-    const long long f0 = (static_cast<long long>(blockIdx.x) * kGroupsPerCta + grp) * kFramesPerCta;
-    if (f0 >= n_frames) break;
-    if (grp > 0) __syncthreads();   // everyone is done with the previous group's samples / spectra
+    // inter-pass twiddles W256^(t * k1): fixed per thread, kept in registers
+    float2 tw[16];
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+        const int j = (t * k1) & 255;
+        tw[k1] = make_float2(__ldg(tables + 400 + 2 * j), __ldg(tables + 400 + 2 * j + 1));
+    }
     float mu = 0.f;
     if (!kPerFrame) {
         // exact integer sum -> mean of the [-1,1) floats (Wav2Win: x - mean(x) over the whole recording)
         const double s = static_cast<double>(static_cast<long long>(*sum_biased) - 32768ll * n_samples);
         mu = static_cast<float>(s / (32768.0 * static_cast<double>(n_samples)));
     }
-    const long long q0 = f0 * kFrameShift - (kFrameLen - kFrameShift) / 2;
-    for (int i = tid; i < kSpan; i += 256) {
-        long long q = q0 + i;
-        long long n = q < 0 ? -q - 1 : (q >= n_samples ? 2 * n_samples - 1 - q : q);  // flip-padding
-        n = n < 0 ? 0 : (n >= n_samples ? n_samples - 1 : n);
-        const float x = static_cast<float>(pcm[n]) * (1.f / 32768.f);
-        if (kPerFrame) {
-            S.samples[i] = x;
+
+    for (int grp = 0; grp < kGroupsPerCta; ++grp) {
+        const long long f0 = (static_cast<long long>(blockIdx.x) * kGroupsPerCta + grp) * kFramesPerCta;
+        if (f0 >= n_frames) break;
+        // ---- stage this group's sample span: 15 * 160 + 400 samples (+ 16 read under the zero tail of the window) ----
+        const long long q0 = f0 * kFrameShift - (kFrameLen - kFrameShift) / 2;
+        const bool fast = q0 >= 1 && q0 + kSpanPad <= n_samples && ((reinterpret_cast<uintptr_t>(pcm + q0) & 15u) == 0);
+        if (fast) {
+            // no reflection inside the span: 16-byte vector loads, every sample read once (+ one neighbour per vector)
+            for (int v = tid; v < kSpanPad / 8; v += 256) {
+                const int16_t* src = pcm + q0 + 8 * v;
+                const uint4 d = __ldg(reinterpret_cast<const uint4*>(src));
+                const int prev = __ldg(src - 1);
+                const uint32_t w4[4] = {d.x, d.y, d.z, d.w};
+                float x[9];
+                x[0] = pcm_to_float(prev);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    x[1 + 2 * e] = pcm_to_float(static_cast<int16_t>(w4[e] & 0xFFFFu));
+                    x[2 + 2 * e] = pcm_to_float(static_cast<int16_t>(w4[e] >> 16));
+                }
+                float y[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (kPerFrame) {
+                        y[e] = x[e + 1];
+                    } else {
+                        const float a = __fsub_rn(x[e + 1], mu), b = __fsub_rn(x[e], mu);
+                        y[e] = __fsub_rn(a, __fmul_rn(0.97f, b));   // pre-emphasis on the whole signal, then framing
+                    }
+                }
+                float4* dst = reinterpret_cast<float4*>(S.samples + 8 * v);
+                dst[0] = make_float4(y[0], y[1], y[2], y[3]);
+                dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+            }
         } else {
-            const float xp = static_cast<float>(pcm[n > 0 ? n - 1 : 0]) * (1.f / 32768.f);
-            const float a = __fsub_rn(x, mu), b = __fsub_rn(xp, mu);
-            S.samples[i] = __fsub_rn(a, __fmul_rn(0.97f, b));  // pre-emphasis on the whole signal, then padding
+            for (int i = tid; i < kSpanPad; i += 256) {
+                long long q = q0 + i;
+                long long n = q < 0 ? -q - 1 : (q >= n_samples ? 2 * n_samples - 1 - q : q);  // flip-padding
+                n = n < 0 ? 0 : (n >= n_samples ? n_samples - 1 : n);
+                const float x = pcm_to_float(pcm[n]);
+                if (kPerFrame) {
+                    S.samples[i] = x;
+                } else {
+                    const float xp = pcm_to_float(pcm[n > 0 ? n - 1 : 0]);
+                    const float a = __fsub_rn(x, mu), b = __fsub_rn(xp, mu);
+                    S.samples[i] = __fsub_rn(a, __fmul_rn(0.97f, b));
+                }
+            }
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    const int fl = tid >> 4;  // frame within the CTA
-    const int t = tid & 15;   // thread within the frame
-    const long long frame = f0 + fl;
-    if (frame >= n_frames) continue;  // whole 16-thread groups skip together; only __syncwarp below
-    const unsigned gmask = 0xFFFFu << (16 * ((tid >> 4) & 1));
-    const float* xs = S.samples + fl * kFrameShift;
-
-    float fmean = 0.f;
-    if (kPerFrame) {
-        float acc = 0.f;
-        for (int i = t; i < kFrameLen; i += 16) acc += xs[i];
+        const long long frame = f0 + fl;
+        if (frame < n_frames) {   // whole 16-thread groups skip together; only __syncwarp(gmask) inside
+            const float* xs = S.samples + fl * kFrameShift;
+            // ---- pass 1: radix-16 over m of z[t + 16 m] (z[n] = x[2n] + i x[2n+1], windowed), then twiddle W256^(t*k1) ----
+            float2 a[16];
+            if (!kPerFrame) {
+                const float2* xs2 = reinterpret_cast<const float2*>(xs) + t;
+                const float2* w2 = reinterpret_cast<const float2*>(S.window) + t;
 #pragma unroll
-        for (int o = 8; o >= 1; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
-        fmean = acc * (1.f / kFrameLen);
-    }
-    auto windowed = [&](int i) -> float {
-        if (i >= kFrameLen) return 0.f;
-        float v;
-        if (kPerFrame) {
-            const float a = __fsub_rn(xs[i], fmean), b = __fsub_rn(xs[i > 0 ? i - 1 : 0], fmean);
-            v = __fsub_rn(a, __fmul_rn(0.97f, b));
-        } else {
-            v = xs[i];
+                for (int m = 0; m < 13; ++m) {
+                    const float2 x = xs2[16 * m], w = w2[16 * m];
+                    a[m] = make_float2(x.x * w.x, x.y * w.y);
+                }
+            } else {
+                float acc = 0.f;
+                for (int i = t; i < kFrameLen; i += 16) acc += xs[i];
+#pragma unroll
+                for (int o = 8; o >= 1; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
+                const float fmean = acc * (1.f / kFrameLen);
+#pragma unroll
+                for (int m = 0; m < 13; ++m) {
+                    const int i = 2 * (t + 16 * m);
+                    const float xm = __fsub_rn(xs[i > 0 ? i - 1 : 0], fmean), x0 = __fsub_rn(xs[i], fmean), x1 = __fsub_rn(xs[i + 1], fmean);
+                    a[m] = make_float2(__fsub_rn(x0, __fmul_rn(0.97f, xm)) * S.window[i], __fsub_rn(x1, __fmul_rn(0.97f, x0)) * S.window[i + 1]);
+                }
+            }
+            a[13] = a[14] = a[15] = make_float2(0.f, 0.f);   // samples 416.. of the zero-padded frame
+            dft16(a);
+            float2* tr = reinterpret_cast<float2*>(S.tr[fl]);
+            tr[t] = a[0];
+#pragma unroll
+            for (int k1 = 1; k1 < 16; ++k1) tr[k1 * 17 + t] = cmul(a[k1], tw[k1]);
+            __syncwarp(gmask);
+            // ---- pass 2: thread k1 = t, radix-16 over t' -> Z[k1 + 16 k2] -------------------------------------------
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = tr[t * 17 + j];
+            dft16(a);
+            __syncwarp(gmask);  // every thread of the frame has read its row of tr: the buffer now holds the power spectrum
+            // ---- real-input untangle + power spectrum.  a[k2] = Z[t + 16 k2]; bin k = t + 16 k2 also needs Z[256 - k], which
+            //      sits in register 15 - k2 of thread 16 - t (thread 0: its own register (16 - k2) & 15) ----------------------
+            float* P = S.tr[fl];
+            const int partner = lane_base | ((16 - t) & 15);
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+                const float2 give = a[15 - k2];
+                float2 zn = make_float2(__shfl_sync(gmask, give.x, partner), __shfl_sync(gmask, give.y, partner));
+                if (t == 0) zn = a[(16 - k2) & 15];
+                const float2 zk = a[k2];
+                const int k = t + 16 * k2;
+                const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));   // (Z[k] + conj Z[N-k]) / 2
+                const float2 d = make_float2(0.5f * (zk.x - zn.x), 0.5f * (zk.y + zn.y));   // (Z[k] - conj Z[N-k]) / 2
+                const float2 o = make_float2(d.y, -d.x);                                    // d / i
+                const float2 wo = cmul(S.tw512[k], o);
+                const float re = e.x + wo.x, im = e.y + wo.y;
+                P[k] = re * re + im * im;
+            }
+            if (t == 0) {   // bin 256: X[256] = Re Z[0] - Im Z[0]
+                const float x = a[0].x - a[0].y;
+                P[kFftHalf] = x * x;
+            }
+            __syncwarp(gmask);
+            // ---- mel filterbank + log, staged behind the power spectrum ---------------------------------------------------
+            for (int k = t; k < F; k += 16) {
+                const float* w = S.melw + S.mel_off[k];
+                const float* p = P + S.mel_lo[k];
+                const int len = S.mel_len[k];
+                float acc = 0.f;
+                for (int j = 0; j < len; ++j) acc = fmaf(p[j], w[j], acc);
+                P[kStageOff + k] = logf(fmaxf(acc, 1.1920928955078125e-07f));  // torch.finfo(float32).eps
+            }
         }
-        return v * S.window[i];
-    };
-
-    // ---- pass 1: radix-16 over m of z[t + 16 m], then twiddle W256^(t*k1) ------------------------------
-    float2 a[16];
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-        const int n = t + 16 * m;
-        a[m] = make_float2(windowed(2 * n), windowed(2 * n + 1));
+        __syncthreads();
+        // ---- the group's 16 x F outputs are contiguous in the feature matrix: coalesced rows -------------------------------
+        {
+            const long long left = n_frames - f0;
+            const int n_out = static_cast<int>(left < kFramesPerCta ? left : kFramesPerCta) * F;
+            float* dst = feats + f0 * F;
+            for (int i = tid; i < n_out; i += 256) {
+                const int fr = i / F;
+                dst[i] = S.tr[fr][kStageOff + (i - fr * F)];
+            }
+        }
+        // (the next group's staging writes S.samples only; its pass 1 follows a __syncthreads)
     }
-    dft16(a);
-    float2* tr = S.tr[fl];
-#pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) tr[k1 * 17 + t] = cmul(a[k1], S.tw256[t * k1]);
-    __syncwarp(gmask);
-    // ---- pass 2: thread k1 = t, radix-16 over t' -> Z[k1 + 16 k2] ----------------------------------------
-#pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = tr[t * 17 + j];
-    dft16(a);
-    __syncwarp(gmask);  // every thread of the frame has read its row of tr: reuse it for Z
-    float2* Z = tr;
-#pragma unroll
-    for (int k2 = 0; k2 < 16; ++k2) Z[t + 16 * k2] = a[k2];
-    __syncwarp(gmask);
-    // ---- real-input untangle + power spectrum ------------------------------------------------------------
-    float* P = S.pw[fl];
-    for (int k = t; k < kBins; k += 16) {
-        const float2 zk = Z[k & 255];
-        const float2 zn = Z[(kFftHalf - k) & 255];
-        const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));   // (Z[k] + conj Z[N-k]) / 2
-        const float2 d = make_float2(0.5f * (zk.x - zn.x), 0.5f * (zk.y + zn.y));   // (Z[k] - conj Z[N-k]) / 2
-        const float2 o = make_float2(d.y, -d.x);                                    // d / i
-        const float2 wo = cmul(S.tw512[k], o);
-        const float re = e.x + wo.x, im = e.y + wo.y;
-        P[k] = re * re + im * im;
-    }
-    __syncwarp(gmask);
-    // ---- mel filterbank + log -----------------------------------------------------------------------------
-    for (int k = t; k < F; k += 16) {
-        const float* w = S.melw + S.mel_off[k];
-        const float* p = P + S.mel_lo[k];
-        float acc = 0.f;
-        for (int j = 0; j < S.mel_len[k]; ++j) acc = fmaf(p[j], w[j], acc);
-        feats[frame * F + k] = logf(fmaxf(acc, 1.1920928955078125e-07f));  // torch.finfo(float32).eps
-    }
-    }  // groups
 }
 
 __global__ void __launch_bounds__(256) pcm_sum_kernel(const int16_t* __restrict__ pcm, long long n,
                                                       unsigned long long* __restrict__ out) {
     long long acc = 0;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
-        acc += pcm[i];
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x, gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    // head up to the first 16-byte boundary, 8 samples per load in the body, scalar tail
+    long long head = ((16 - (reinterpret_cast<uintptr_t>(pcm) & 15u)) & 15u) / 2;
+    if (head > n) head = n;
+    const long long n_vec = (n - head) / 8;
+    for (long long i = gid; i < head; i += stride) acc += pcm[i];
+    const uint4* pv = reinterpret_cast<const uint4*>(pcm + head);
+    for (long long i = gid; i < n_vec; i += stride) {
+        const uint4 d = __ldg(pv + i);
+        const uint32_t w4[4] = {d.x, d.y, d.z, d.w};
+        int part = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) part += static_cast<int16_t>(w4[e] & 0xFFFFu) + static_cast<int16_t>(w4[e] >> 16);
+        acc += part;
+    }
+    for (long long i = head + 8 * n_vec + gid; i < n; i += stride) acc += pcm[i];
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     __shared__ long long s_part[8];
@@ -215,7 +292,7 @@ cudaError_t launch_pcm_sum(const int16_t* pcm, long long n, unsigned long long* 
     const unsigned long long bias = 32768ull * static_cast<unsigned long long>(n);
     cudaError_t e = cudaMemcpyAsync(sum_biased, &bias, sizeof(bias), cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
-    long long blocks = (n + 256 * 16 - 1) / (256 * 16);
+    long long blocks = (n + 256 * 64 - 1) / (256 * 64);
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     pcm_sum_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(pcm, n, sum_biased);
@@ -225,21 +302,28 @@ cudaError_t launch_pcm_sum(const int16_t* pcm, long long n, unsigned long long* 
 cudaError_t launch_fbank(const int16_t* pcm, long long n_samples, long long n_frames, const unsigned long long* sum_biased,
                          int per_frame, const FbankMel& mel, const float* tables, float* feats, cudaStream_t stream) {
     if (n_frames <= 0) return cudaSuccess;
+    static const int occ = []() { const char* v = std::getenv("LD_FBANK_OCC"); const int o = v ? std::atoi(v) : 3; return o < 2 ? 2 : (o > 4 ? 4 : o); }();
     static PerDeviceOnce attr_set;
+    const int smem = static_cast<int>(sizeof(FbankSmem));
     if (!attr_set.flag()) {
-        cudaError_t e = cudaFuncSetAttribute(fbank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(sizeof(FbankSmem)));
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(fbank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(sizeof(FbankSmem)));
+        cudaError_t e = cudaSuccess;
+#define LD_FBANK_ATTR(pf, mb) \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fbank_kernel<pf, mb>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+        LD_FBANK_ATTR(false, 2); LD_FBANK_ATTR(false, 3); LD_FBANK_ATTR(false, 4);
+        LD_FBANK_ATTR(true, 2); LD_FBANK_ATTR(true, 3); LD_FBANK_ATTR(true, 4);
+#undef LD_FBANK_ATTR
         if (e != cudaSuccess) return e;
         attr_set.flag() = true;
     }
     const unsigned grid = static_cast<unsigned>((n_frames + kFramesPerCta * kGroupsPerCta - 1) / (kFramesPerCta * kGroupsPerCta));
-    if (per_frame)
-        fbank_kernel<true><<<grid, 256, sizeof(FbankSmem), stream>>>(pcm, n_samples, n_frames, sum_biased, mel, tables, feats);
-    else
-        fbank_kernel<false><<<grid, 256, sizeof(FbankSmem), stream>>>(pcm, n_samples, n_frames, sum_biased, mel, tables, feats);
+#define LD_FBANK_LAUNCH(pf, mb) \
+    fbank_kernel<pf, mb><<<grid, 256, smem, stream>>>(pcm, n_samples, n_frames, sum_biased, mel, tables, feats)
+    if (per_frame) {
+        if (occ == 2) LD_FBANK_LAUNCH(true, 2); else if (occ == 3) LD_FBANK_LAUNCH(true, 3); else LD_FBANK_LAUNCH(true, 4);
+    } else {
+        if (occ == 2) LD_FBANK_LAUNCH(false, 2); else if (occ == 3) LD_FBANK_LAUNCH(false, 3); else LD_FBANK_LAUNCH(false, 4);
+    }
+#undef LD_FBANK_LAUNCH
     return cudaGetLastError();
 }
 

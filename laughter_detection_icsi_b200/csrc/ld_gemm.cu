@@ -27,6 +27,7 @@
 // fp32 by the tensor core (exact), so it travels through the same TMA/smem pipeline as every other operand.
 // The launch description is a __grid_constant__ parameter, so tile/job/tap bookkeeping runs on the uniform datapath.
 #include <cstdio>
+#include <cstdlib>
 
 #include <cuda_bf16.h>
 
@@ -98,6 +99,9 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
     constexpr int kChunks = CIN / 8;   // 16-byte channel chunks per pixel
     constexpr int kSteps = CIN / 16;   // MMAs (K = 16) per tap
     const long long t_cta0 = clock64();
+    // PDL: the next conv launch may be scheduled onto SMs as the CTAs of this grid exit; its prologue (barriers, TMEM, weights)
+    // then overlaps this grid's tail.  It reads/writes planes only after griddep_wait() below.
+    if (threadIdx.x == 0) griddep_launch_dependents();
 
     const int n_wtaps = L.n_wtaps, ext_alloc = L.ext_alloc, n_stages = L.n_stages, gps = L.groups_per_stage;
     const GemmSmem lay = gemm_smem_layout(CIN, COUT, n_wtaps, L.n_jobs, ext_alloc, gps, n_stages);
@@ -160,6 +164,7 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
     unsigned long long* prof = L.prof;
     const bool profiling = prof != nullptr;
 
+    if (warp != 0) griddep_wait();   // (warp 0 first issues the loads of the launch constants -- weights, job table -- below)
     if (warp < kProducers) {
         // ------------------------------------------------------------------ producers
         if (warp == 0) {
@@ -188,6 +193,7 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
                     bulk_g2s(w_addr + t * tap_bytes, wsrc + static_cast<size_t>(t) * tap_bytes, tap_bytes, bar_w);
             }
         }
+        if (warp == 0) griddep_wait();   // the previous kernel's planes are complete and visible from here on
         mbar_wait(bar_w, 0);   // the job table (and the weights) are in shared memory
         const uint32_t lbo_a = static_cast<uint32_t>(ext_alloc) * 16u;  // bytes between channel chunks of a group
         // Two independent pipelines: producer w fills ring w (stages [w * ring_n, (w + 1) * ring_n)) with the tiles
@@ -496,8 +502,18 @@ static cudaError_t launch_typed(const GemmLaunch& h, int m_tiles, int M, int num
     // every job kind (jobs differ in cost: chains of several outputs, the interior plane)
     auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
     while (total > grid && grid > 1 && gcd(grid, h.n_jobs) != 1) --grid;
-    gemm_taps_kernel<CIN, COUT, MODE><<<grid, kGemmThreads, lay.total, stream>>>(static_cast<const GemmParams&>(h), m_tiles, M);
-    return cudaGetLastError();
+    static const bool pdl = []() { const char* v = std::getenv("LD_GEMM_PDL"); return v == nullptr || std::atoi(v) != 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = lay.total;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, gemm_taps_kernel<CIN, COUT, MODE>, static_cast<const GemmParams&>(h), m_tiles, M);
 }
 
 cudaError_t launch_gemm_taps(GemmLaunch& h, int m_tiles, int M, int num_sms, cudaStream_t stream) {

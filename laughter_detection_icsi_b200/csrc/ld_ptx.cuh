@@ -115,6 +115,11 @@ __device__ __forceinline__ void umma_f16_ss_pred(uint32_t d_tmem, uint64_t a_des
     // (volatile, but no "memory" clobber: the MMA touches no C++-visible memory; its ordering against the mbarrier waits and
     //  commits around it -- all volatile asm -- is kept, while plain loads of the next taps may be scheduled across it)
 }
+// Programmatic dependent launch: the next kernel of the stream may start its prologue while this grid drains
+// (launch_dependents), and must not touch memory other kernels produce or consume before wait() returns.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void umma_commit_pred(uint32_t bar, bool issue) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t"

@@ -223,8 +223,10 @@ def test_split_precision_meets_2e3_on_the_calibrated_checkpoint():
         assert np.abs(p_gpu - p_emu).max() < 2e-4   # same rounding model; fp32 summation order differs
         for tag in ("block2.0.h.int", "block2.1.y.int.e", "block3.1.y.r0.e", "block4.1.y.r5"):
             pl = next(p for p in plan["planes"] if p["tag"] == tag)
-            got = eng.read_plane(pl["id"], nb + 100, pl["wp"], pl["C"])
-            want = emu.plane_as_rows(pl["id"], nb + 100).numpy()
+            # rows past the window starts are either halo the emulator computes from zeros and the GPU from whatever an earlier
+            # call left there (never consumed by a real window) -- compare the rows every window start owns
+            got = eng.read_plane(pl["id"], nb + 100, pl["wp"], pl["C"])[:nb]
+            want = emu.plane_as_rows(pl["id"], nb + 100).numpy()[:nb]
             scale = np.abs(want).max()
             assert np.abs(got - want).max() < 2e-4 * scale, tag
         # random-init weights: far inside the 1e-3 of the north star
