@@ -170,20 +170,20 @@ def time_training(local_rank, world, batch, steps, warmup):
     for s in range(4):
         b = ld_train.synthetic_lad_batch(batch, seed=1000 * rank + s)
         batches.append({k: v.pin_memory() for k, v in b.items()})
-    stepper = ld_train.make_stepper(model, opt, dev, world_size=world)
-    loss = 0.0
+    stepper = ld_train.make_stepper(model, opt, dev, world_size=world, graph=os.environ.get("LD_TRAIN_GRAPH", "1") != "0")
     for i in range(max(warmup, 3)):
-        loss = stepper(batches[i % 4])[0]
+        stepper(batches[i % 4])
+    stepper.flush()
     torch.cuda.synchronize()
-    eng = model._train_engine(batch)
-    l0 = eng.train_kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    m = None
     for i in range(steps):
-        loss = stepper(batches[i % 4])[0]
+        m = stepper(batches[i % 4]) or m
+    m = stepper.flush() or m   # (inside the clock: every step's loss / accuracy reaches the host)
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps, float(loss), (eng.train_kernel_launches - l0) / max(steps, 1), stepper.mode
+    return e0.elapsed_time(e1) / steps, float(m[0]), stepper.launches_per_step, stepper.mode
 
 
 # ----------------------------------------------------------------------------------------------------- parity (outside the timed region)
@@ -426,7 +426,8 @@ def run_b200(args):
                              "note": "3 x 1.41666 GFLOP per sample (forward, data gradient, weight gradient) over the WHOLE step time, "
                                      "BatchNorm/element-wise passes, head, optimiser and H2D included"},
                 "includes": "H2D of the batch from pinned host memory, forward, backward, flat-bucket gradient all-reduce (N>1), "
-                            "fused clip_grad_norm_ 1.0 + Adam (ld_clip_adam_step), per-step loss/accuracy read-back like train.py:297",
+                            "fused clip_grad_norm_ 1.0 + Adam (ld_clip_adam_step_dev), per-step loss/accuracy/precision/recall read-back "
+                            "like train.py:297 (fetched one step late so that the host never drains the stream)",
                 "data": "synthetic LAD windows (100 x 44 log-mel-like), labels recoverable"}
         if n_gpus == 1 and not args.no_parity:
             line["parity"] = parity_report(pipe, sd, pcm_dev[: min(n_samples, 9600000)].contiguous(), thresholds, min_lengths)

@@ -161,6 +161,10 @@ LD_API int64_t ld_train_kernel_launches(const ld_ctx* ctx);
  * device) receives the un-clipped global L2 norm.  For data-parallel training all-reduce grads_d before the call. */
 LD_API int ld_clip_adam_step(ld_ctx* ctx, float* params_d, const float* grads_d, float* exp_avg_d, float* exp_avg_sq_d, int64_t n,
                       float max_norm, float lr, float beta1, float beta2, float eps, int64_t step, float* grad_norm_d, void* stream);
+/* Same update with the step count kept in DEVICE memory: *step_d (int64, starts at 0) is incremented by the call and the bias
+ * corrections are computed on the device, so a CUDA graph that captured the call replays correctly step after step. */
+LD_API int ld_clip_adam_step_dev(ld_ctx* ctx, float* params_d, const float* grads_d, float* exp_avg_d, float* exp_avg_sq_d, int64_t n,
+                          float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_d, float* grad_norm_d, void* stream);
 /* Debug: sum |value| of every conv output, activation, conv-output gradient and input-gradient plane of the last step. */
 LD_API int32_t ld_train_debug_checksums(ld_ctx* ctx, double* out, int32_t cap);
 /* Debug: one tensor of the last training step as dense (B, C, H, W) fp32 in host memory.  kind 0: conv output z of conv

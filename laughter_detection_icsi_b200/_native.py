@@ -77,6 +77,8 @@ SIGNATURES = {
     "ld_train_kernel_launches": (c_int64, [c_void_p]),
     "ld_clip_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                            ctypes.c_float, ctypes.c_float, c_int64, c_void_p, c_void_p]),
+    "ld_clip_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                               ctypes.c_float, ctypes.c_float, c_void_p, c_void_p, c_void_p]),
     "ld_train_debug_read": (c_int64, [c_void_p, c_int32, c_int32, c_void_p, POINTER(c_int32)]),
     "ld_train_debug_checksums": (c_int32, [c_void_p, POINTER(c_double), c_int32]),
     "ld_debug_gemm_counters": (c_int32, [c_void_p, POINTER(ctypes.c_uint64), c_int32, c_int32]),

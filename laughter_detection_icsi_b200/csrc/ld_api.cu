@@ -143,7 +143,7 @@ struct ld_ctx {
     ld::FbankMel mel{};
     unsigned long long* pcm_sum = nullptr;
     // scratch
-    DeviceBuf chan_table, seg_scratch, iir_scratch, thr_buf;
+    DeviceBuf chan_table, seg_scratch, iir_scratch, thr_buf, adam_scratch;
     DeviceBuf e2e_pcm, e2e_feats, e2e_probs, e2e_mel;
     long long launches = 0;
     // optional per-class device timing
@@ -551,7 +551,7 @@ void ld_destroy(ld_ctx* ctx) {
     ctx->mel_sparse.release(); ctx->chan_table.release(); ctx->seg_scratch.release(); ctx->iir_scratch.release();
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    ctx->thr_buf.release(); ctx->e2e_pcm.release(); ctx->e2e_feats.release(); ctx->e2e_probs.release(); ctx->e2e_mel.release();
+    ctx->thr_buf.release(); ctx->adam_scratch.release(); ctx->e2e_pcm.release(); ctx->e2e_feats.release(); ctx->e2e_probs.release(); ctx->e2e_mel.release();
     delete ctx;
 }
 
@@ -676,6 +676,8 @@ int ld_fbank_i16(ld_ctx* ctx, const int16_t* pcm_d, const int64_t* chan_len, int
         LD_CUDA(cudaMemcpyAsync(m.data(), mel_d, m.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
         LD_CUDA(cudaStreamSynchronize(stream));
         if (m != ctx->mel_host) {
+            // per filter: its run of non-zero bins, widened to 4-bin alignment so that the kernel reads power values and weights
+            // as 16-byte vectors (zero weights on the padding); lo = first bin (multiple of 4), len = vectors, off = offset in w
             std::vector<float> w;
             std::vector<int> lo(F), len(F), off(F);
             for (int k = 0; k < F; ++k) {
@@ -683,8 +685,9 @@ int ld_fbank_i16(ld_ctx* ctx, const int16_t* pcm_d, const int64_t* chan_len, int
                 for (int j = 0; j < 257; ++j)
                     if (m[static_cast<size_t>(j) * F + k] != 0.f) { if (a < 0) a = j; b = j; }
                 if (a < 0) { a = 0; b = 0; }
-                lo[k] = a; len[k] = b - a + 1; off[k] = static_cast<int>(w.size());
-                for (int j = a; j <= b; ++j) w.push_back(m[static_cast<size_t>(j) * F + k]);
+                const int a4 = a & ~3, n4 = (b - a4) / 4 + 1;
+                lo[k] = a4; len[k] = n4; off[k] = static_cast<int>(w.size());
+                for (int j = a4; j < a4 + 4 * n4; ++j) w.push_back(j < 257 ? m[static_cast<size_t>(j) * F + k] : 0.f);
             }
             if (w.size() > 1024 || F > 64) return fail(LD_ERR_UNSUPPORTED, "filterbank has too many non-zero weights");
             const size_t bytes = w.size() * sizeof(float) + 3 * F * sizeof(int);
@@ -950,9 +953,28 @@ int ld_clip_adam_step(ld_ctx* ctx, float* params_d, const float* grads_d, float*
     if (!ctx || !params_d || !grads_d || !exp_avg_d || !exp_avg_sq_d || n <= 0 || step < 1) return fail(LD_ERR_INVALID, "bad arguments");
     LD_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    if (int r = ctx->thr_buf.ensure(64)) return r;
-    float* scratch = static_cast<float*>(ctx->thr_buf.p);
+    if (int r = ctx->adam_scratch.ensure(64)) return r;   // (its own buffer: a captured graph keeps the address)
+    float* scratch = static_cast<float*>(ctx->adam_scratch.p);
     LD_CUDA(ld::clip_adam_step(params_d, grads_d, exp_avg_d, exp_avg_sq_d, n, max_norm, lr, beta1, beta2, eps, step, scratch, stream));
+    if (grad_norm_d) LD_CUDA(cudaMemcpyAsync(grad_norm_d, scratch + 1, sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    return LD_OK;
+}
+
+int ld_clip_adam_step_dev(ld_ctx* ctx, float* params_d, const float* grads_d, float* exp_avg_d, float* exp_avg_sq_d, int64_t n, float max_norm,
+                          float lr, float beta1, float beta2, float eps, int64_t* step_d, float* grad_norm_d, void* stream_v) {
+    if (!ctx || !params_d || !grads_d || !exp_avg_d || !exp_avg_sq_d || !step_d || n <= 0) return fail(LD_ERR_INVALID, "bad arguments");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (ctx->adam_scratch.p == nullptr) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cap);
+        if (cap != cudaStreamCaptureStatusNone) return fail(LD_ERR_STATE, "first optimiser step inside a CUDA graph capture: run one eager step first");
+        if (int r = ctx->adam_scratch.ensure(64)) return r;
+    }
+    float* scratch = static_cast<float*>(ctx->adam_scratch.p);
+    static_assert(sizeof(long long) == sizeof(int64_t), "step counter type");
+    LD_CUDA(ld::clip_adam_step_dev(params_d, grads_d, exp_avg_d, exp_avg_sq_d, n, max_norm, lr, beta1, beta2, eps,
+                                   reinterpret_cast<long long*>(step_d), scratch, stream));
     if (grad_norm_d) LD_CUDA(cudaMemcpyAsync(grad_norm_d, scratch + 1, sizeof(float), cudaMemcpyDeviceToDevice, stream));
     return LD_OK;
 }

@@ -65,16 +65,17 @@ __device__ __forceinline__ void dft16(float2 (&a)[16]) {
 
 constexpr int kSpanPad = kSpan + 16;    // pass 1 reads 416 samples per frame (the window is zero past 400)
 constexpr int kWinPad = kFrameLen + 16;
-constexpr int kTrFloats = 2 * 16 * 17;   // floats of one frame's transpose buffer (16 x 17 complex)
+constexpr int kTrFloats = 2 * 16 * 17 + 16;   // floats of one frame's transpose buffer (16 x 17 complex) + 16: the two frames of
+                                              // a warp sit 16 banks apart, so their power-spectrum accesses do not collide
 constexpr int kStageOff = 264;           // floats: the frame's 44 log-mel outputs wait here (behind its 257 power values)
 
 struct FbankSmem {
     float samples[kSpanPad];                   // pre-processed (utterance mode) or raw (frame mode) samples
     float window[kWinPad];                     // Povey window, zero-padded to 416
     float2 tw512[kBins];
-    float tr[kFramesPerCta][kTrFloats];        // per frame: transpose buffer between the two radix-16 passes, then the power
+    __align__(16) float tr[kFramesPerCta][kTrFloats];   // per frame: transpose buffer between the two radix-16 passes, then the power
                                                // spectrum (257 floats) and the staged outputs (aliased: the passes are done)
-    float melw[kMaxMelWeights];
+    __align__(16) float melw[kMaxMelWeights];
     int mel_lo[kMaxFilters], mel_len[kMaxFilters], mel_off[kMaxFilters];
 };
 
@@ -225,18 +226,22 @@ fbank_kernel(const int16_t* __restrict__ pcm, long long n_samples, long long n_f
                 const float re = e.x + wo.x, im = e.y + wo.y;
                 P[k] = re * re + im * im;
             }
-            if (t == 0) {   // bin 256: X[256] = Re Z[0] - Im Z[0]
+            if (t == 0) {   // bin 256: X[256] = Re Z[0] - Im Z[0]; bins 257..259 only ever meet zero weights
                 const float x = a[0].x - a[0].y;
                 P[kFftHalf] = x * x;
+                P[257] = P[258] = P[259] = 0.f;
             }
             __syncwarp(gmask);
             // ---- mel filterbank + log, staged behind the power spectrum ---------------------------------------------------
             for (int k = t; k < F; k += 16) {
-                const float* w = S.melw + S.mel_off[k];
-                const float* p = P + S.mel_lo[k];
-                const int len = S.mel_len[k];
+                const float4* w4 = reinterpret_cast<const float4*>(S.melw + S.mel_off[k]);
+                const float4* p4 = reinterpret_cast<const float4*>(P + S.mel_lo[k]);
+                const int n4 = S.mel_len[k];
                 float acc = 0.f;
-                for (int j = 0; j < len; ++j) acc = fmaf(p[j], w[j], acc);
+                for (int j = 0; j < n4; ++j) {   // 16-byte vectors of power values and weights (runs are padded to 4 bins)
+                    const float4 pv = p4[j], wv = w4[j];
+                    acc = fmaf(pv.x, wv.x, acc); acc = fmaf(pv.y, wv.y, acc); acc = fmaf(pv.z, wv.z, acc); acc = fmaf(pv.w, wv.w, acc);
+                }
                 P[kStageOff + k] = logf(fmaxf(acc, 1.1920928955078125e-07f));  // torch.finfo(float32).eps
             }
         }

@@ -29,32 +29,33 @@ __device__ __forceinline__ int find_channel(const ChannelTable& ct, long long s,
     return (local >= 0 && local < ct.frames[lo]) ? lo : -1;
 }
 
-// One thread computes kStemPx consecutive pixels of a row for all 64 channels: every weight fetched from shared memory is
-// used kStemPx times (the one-pixel version was bound by its 576 shared-memory loads per pixel).
+// One thread computes kStemPx consecutive pixels of one GLOBAL feature row for all 64 channels, keeping the three kernel-row
+// partial sums s_ky apart: every stem plane (interior: s0 + s1 + s2; top edge of a window: s1 + s2; bottom edge: s0 + s1 at
+// row + 99) is a masked sum of them, so the 3 x 3 taps are multiplied once for all planes instead of once per plane
+// (9 instead of 21 multiply-adds per pixel and channel), and the feature patch is read once.
 constexpr int kStemPx = 4;
 __global__ void __launch_bounds__(256)
-stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long long chunk_row0, int rows) {
+stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long long chunk_row0, int rows, int row_lo, int rows_total) {
     __shared__ float s_w[64 * 9];
     __shared__ float s_scale[64], s_shift[64];
     for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) s_w[i] = L.w[i];
     for (int i = threadIdx.x; i < 64; i += blockDim.x) { s_scale[i] = L.scale[i]; s_shift[i] = L.shift[i]; }
     __syncthreads();
 
-    const StemJob job = L.jobs[blockIdx.y];
     const int wp = L.W + 2;
     const int groups_per_row = (wp + kStemPx - 1) / kStemPx;
     const long long gi = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (gi >= static_cast<long long>(rows) * groups_per_row) return;
-    const long long r = gi / groups_per_row;
-    const int pc0 = static_cast<int>(gi - r * groups_per_row) * kStemPx;   // first padded column of this thread
+    if (gi >= static_cast<long long>(rows_total) * groups_per_row) return;
+    const int rr = static_cast<int>(gi / groups_per_row);
+    const int G = row_lo + rr;                                              // chunk-relative global row of the centre tap
+    const int pc0 = static_cast<int>(gi - static_cast<long long>(rr) * groups_per_row) * kStemPx;   // first padded column
 
     // the 3 x (kStemPx + 2) input patch; real column = padded column - 1
     float x[3][kStemPx + 2];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         long long local = 0;
-        const long long s = chunk_row0 + r + job.row_shift + ky - 1;
-        const int c = ((job.mask >> ky) & 1) ? find_channel(ct, s, local) : -1;
+        const int c = find_channel(ct, chunk_row0 + G + ky - 1, local);
         const float* frow = (c >= 0) ? feats + (ct.feat_off[c] + local) * L.W : nullptr;
 #pragma unroll
         for (int k = 0; k < kStemPx + 2; ++k) {
@@ -62,35 +63,56 @@ stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long
             x[ky][k] = (frow != nullptr && cc >= 0 && cc < L.W) ? __ldg(frow + cc) : 0.f;
         }
     }
-    float acc[kStemPx][8];
+    // plane row this global row lands on, per job (row = G - row_shift), or -1
+    int prow[kMaxStemJobs];
+#pragma unroll
+    for (int j = 0; j < kMaxStemJobs; ++j) {
+        const int r = G - (j < L.n_jobs ? L.jobs[j].row_shift : 0);
+        prow[j] = (j < L.n_jobs && r >= 0 && r < rows) ? r : -1;
+    }
     for (int kc = 0; kc < 8; ++kc) {
+        float part[3][kStemPx][8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int ch = kc * 8 + e;
             float w[9];
 #pragma unroll
             for (int t = 0; t < 9; ++t) w[t] = s_w[ch * 9 + t];
-            const float sc = s_scale[ch], sh = s_shift[ch];
 #pragma unroll
-            for (int px = 0; px < kStemPx; ++px) {
-                float a = 0.f;
+            for (int px = 0; px < kStemPx; ++px)
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+                for (int ky = 0; ky < 3; ++ky) {
+                    float a = 0.f;
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) a = fmaf(w[ky * 3 + kx], x[ky][px + kx], a);
-                acc[px][e] = fmaxf(fmaf(a, sc, sh), 0.f);
-            }
+                    part[ky][px][e] = a;
+                }
         }
 #pragma unroll
-        for (int px = 0; px < kStemPx; ++px) {
-            const int pc = pc0 + px;
-            if (pc >= wp) continue;
-            uint4 ov;
-            __half2* oh = reinterpret_cast<__half2*>(&ov);
-            const bool pad = pc == 0 || pc == wp - 1;
+        for (int j = 0; j < kMaxStemJobs; ++j) {
+            if (prow[j] < 0) continue;
+            const StemJob job = L.jobs[j];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) oh[e] = pad ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(acc[px][2 * e], acc[px][2 * e + 1]);
-            *reinterpret_cast<uint4*>(job.out + (r * wp + pc) * 8 + kc * job.kc_stride) = ov;
+            for (int px = 0; px < kStemPx; ++px) {
+                const int pc = pc0 + px;
+                if (pc >= wp) continue;
+                const bool pad = pc == 0 || pc == wp - 1;
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    // same order of additions as a per-plane evaluation: ky ascending over the rows the plane sees
+                    float a = 0.f;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+                        if ((job.mask >> ky) & 1) a += part[ky][px][e];
+                    o[e] = fmaxf(fmaf(a, s_scale[kc * 8 + e], s_shift[kc * 8 + e]), 0.f);
+                }
+                uint4 ov;
+                __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) oh[e] = pad ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(o[2 * e], o[2 * e + 1]);
+                *reinterpret_cast<uint4*>(job.out + (static_cast<long long>(prow[j]) * wp + pc) * 8 + kc * job.kc_stride) = ov;
+            }
         }
     }
 }
@@ -157,9 +179,12 @@ head_kernel(HeadLaunch L, ChannelTable ct, float* __restrict__ probs, long long 
 
 cudaError_t launch_stem(const StemLaunch& L, const ChannelTable& ct, const float* feats, long long chunk_row0,
                         int rows, cudaStream_t stream) {
-    const long long groups = static_cast<long long>(rows) * ((L.W + 2 + kStemPx - 1) / kStemPx);
-    dim3 grid(static_cast<unsigned>((groups + 255) / 256), L.n_jobs);
-    stem_kernel<<<grid, 256, 0, stream>>>(L, ct, feats, chunk_row0, rows);
+    // global rows whose taps reach some plane row: [min row_shift, rows + max row_shift)
+    int lo = 0, hi = 0;
+    for (int j = 0; j < L.n_jobs; ++j) { lo = j == 0 ? L.jobs[j].row_shift : (L.jobs[j].row_shift < lo ? L.jobs[j].row_shift : lo); hi = L.jobs[j].row_shift > hi ? L.jobs[j].row_shift : hi; }
+    const int rows_total = rows + hi - lo;
+    const long long groups = static_cast<long long>(rows_total) * ((L.W + 2 + kStemPx - 1) / kStemPx);
+    stem_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, stream>>>(L, ct, feats, chunk_row0, rows, lo, rows_total);
     return cudaGetLastError();
 }
 

@@ -83,10 +83,10 @@ bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& jobs, const Ge
 
 // ld_fbank.cu
 struct FbankMel {           // sparse view of the (257, F) filterbank, built from the caller's matrix
-    const float* weights;   // packed nonzero runs, filter after filter
-    const int* lo;          // [F] first bin of filter k's run
-    const int* len;         // [F] run length
-    const int* off;         // [F] offset of the run inside weights
+    const float* weights;   // packed runs of 4-bin vectors, filter after filter (zero weights on the alignment padding)
+    const int* lo;          // [F] first bin of filter k's run (multiple of 4)
+    const int* len;         // [F] run length in 4-bin vectors
+    const int* off;         // [F] offset of the run inside weights (multiple of 4)
     int n_filters;
 };
 cudaError_t launch_pcm_sum(const int16_t* pcm, long long n, unsigned long long* sum_biased, cudaStream_t stream);

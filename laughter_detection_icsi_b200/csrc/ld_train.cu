@@ -703,6 +703,7 @@ public:
     float* head_scratch = nullptr;
     BnFinalizeItem* bn_items = nullptr;
     std::vector<BnFinalizeItem> bn_items_host;
+    int bn_items_batch = -1;          // batch size the device copy of the table was built for
     float *x_keep = nullptr, *mask1_keep = nullptr, *mask2_keep = nullptr, *params_keep = nullptr;   // inputs of the last forward
     HeadScratch hs{};
     float *dl1 = nullptr, *dd1 = nullptr, *dpool = nullptr;
@@ -1232,11 +1233,20 @@ cudaError_t train_forward(TrainNet* n, const float* params, const float* x, int 
     LD_TRY(cudaGetLastError());
     // conv BatchNorm statistics (mean incl. conv bias, biased variance) for the caller's running-statistics update
     {
-        std::vector<BnFinalizeItem>& items = n->bn_items_host;   // persistent: the async copy may read it after we return
-        items.clear();
-        for (const auto& c : n->convs)
-            items.push_back({c.bn.fwd_sums, c.bn.stat_out, c.bn.C, c.b_off, 1.f / static_cast<float>(c.bn.count)});
-        LD_TRY(cudaMemcpyAsync(n->bn_items, items.data(), items.size() * sizeof(BnFinalizeItem), cudaMemcpyHostToDevice, stream));
+        // the table depends on the batch size only: uploaded (synchronously, pageable host memory) when B changes, so that the
+        // steady-state step has no host->device copy and can be captured into a CUDA graph
+        std::vector<BnFinalizeItem>& items = n->bn_items_host;
+        if (n->bn_items_batch != B) {
+            items.clear();
+            for (const auto& c : n->convs)
+                items.push_back({c.bn.fwd_sums, c.bn.stat_out, c.bn.C, c.b_off, 1.f / static_cast<float>(c.bn.count)});
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(stream, &cap);
+            if (cap != cudaStreamCaptureStatusNone) { err = "first training step of a batch size inside a CUDA graph capture: run one eager step first"; return cudaErrorInvalidValue; }
+            LD_TRY(cudaStreamSynchronize(stream));
+            LD_TRY(cudaMemcpy(n->bn_items, items.data(), items.size() * sizeof(BnFinalizeItem), cudaMemcpyHostToDevice));
+            n->bn_items_batch = B;
+        }
         bn_finalize_kernel<<<static_cast<unsigned>(items.size()), 64, 0, stream>>>(n->bn_items, static_cast<int>(items.size()), n->stats, params, bn_stats);
         ++n->launches;
         LD_TRY(cudaGetLastError());
@@ -1324,10 +1334,17 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
         atomicAdd(out, t);
     }
 }
+// step_d != nullptr: the step count lives in device memory (it was incremented before this launch), so that a captured CUDA
+// graph of the training step replays with the right bias corrections.
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
                  const float* __restrict__ sumsq, float max_norm, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-                 float* __restrict__ norm_out) {
+                 float* __restrict__ norm_out, const long long* __restrict__ step_d) {
+    if (step_d != nullptr) {
+        const float st = static_cast<float>(*step_d);
+        bc1 = 1.f - powf(b1, st);
+        bc2_sqrt = sqrtf(1.f - powf(b2, st));
+    }
     const float norm = sqrtf(*sumsq);
     const float scale = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
     if (norm_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = norm;
@@ -1350,7 +1367,20 @@ cudaError_t clip_adam_step(float* params, const float* grads, float* m, float* v
     sumsq_kernel<<<grid, 256, 0, stream>>>(grads, n, scratch2);
     const float bc1 = 1.f - std::pow(b1, static_cast<float>(step));
     const float bc2 = 1.f - std::pow(b2, static_cast<float>(step));
-    clip_adam_kernel<<<grid, 256, 0, stream>>>(params, grads, m, v, n, scratch2, max_norm, lr, b1, b2, eps, bc1, std::sqrt(bc2), scratch2 + 1);
+    clip_adam_kernel<<<grid, 256, 0, stream>>>(params, grads, m, v, n, scratch2, max_norm, lr, b1, b2, eps, bc1, std::sqrt(bc2), scratch2 + 1, nullptr);
+    return cudaGetLastError();
+}
+
+namespace {
+__global__ void step_increment_kernel(long long* step, float* sumsq) { *step += 1; *sumsq = 0.f; }
+}  // namespace
+
+cudaError_t clip_adam_step_dev(float* params, const float* grads, float* m, float* v, long long n, float max_norm, float lr, float b1,
+                               float b2, float eps, long long* step_d, float* scratch2, cudaStream_t stream) {
+    step_increment_kernel<<<1, 1, 0, stream>>>(step_d, scratch2);
+    const unsigned grid = static_cast<unsigned>(std::max<long long>(1, std::min<long long>((n + 255) / 256, 592)));
+    sumsq_kernel<<<grid, 256, 0, stream>>>(grads, n, scratch2);
+    clip_adam_kernel<<<grid, 256, 0, stream>>>(params, grads, m, v, n, scratch2, max_norm, lr, b1, b2, eps, 1.f, 1.f, scratch2 + 1, step_d);
     return cudaGetLastError();
 }
 

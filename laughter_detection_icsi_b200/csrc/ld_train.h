@@ -70,6 +70,9 @@ long long train_kernel_launches(const TrainNet* net);
 // K8: clip_grad_norm_(max_norm) + Adam step on flat fp32 vectors (scratch2: 2 device floats; [1] receives the gradient norm).
 cudaError_t clip_adam_step(float* params, const float* grads, float* m, float* v, long long n, float max_norm, float lr, float b1,
                            float b2, float eps, long long step, float* scratch2, cudaStream_t stream);
+// Same with the step count in device memory (incremented by the call): replayable from a captured CUDA graph.
+cudaError_t clip_adam_step_dev(float* params, const float* grads, float* m, float* v, long long n, float max_norm, float lr, float b1,
+                               float b2, float eps, long long* step_d, float* scratch2, cudaStream_t stream);
 int train_debug_checksums(TrainNet* net, double* out, int cap);
 long long train_debug_read(TrainNet* net, int kind, int index, float* out, int* dims4);
 

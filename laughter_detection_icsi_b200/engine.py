@@ -291,6 +291,20 @@ class Engine:
                                              params.numel(), float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps),
                                              int(step), grad_norm_out.data_ptr() if grad_norm_out is not None else None, self._stream()))
 
+    def clip_adam_step_dev(self, params, grads, exp_avg, exp_avg_sq, step_d, max_norm=1.0, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                           grad_norm_out=None):
+        """K8 with the step counter in device memory (int64 CUDA tensor, incremented by the call): graph-capturable."""
+        for t in (params, grads, exp_avg, exp_avg_sq):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == params.numel()):
+                raise ValueError("clip_adam_step needs contiguous float32 CUDA vectors of equal length")
+        if not (step_d.is_cuda and step_d.dtype == torch.int64 and step_d.numel() == 1):
+            raise ValueError("step_d must be a one-element int64 CUDA tensor")
+        with torch.cuda.device(self.device):
+            check(self.lib.ld_clip_adam_step_dev(self._h, params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                                 params.numel(), float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                                 step_d.data_ptr(), grad_norm_out.data_ptr() if grad_norm_out is not None else None,
+                                                 self._stream()))
+
     def train_debug_read(self, kind, index):
         """Dense (B, C, H, W) float32 numpy copy of one training tensor (see ld_train_debug_read)."""
         dims = (ctypes.c_int32 * 4)()

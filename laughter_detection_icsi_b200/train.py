@@ -93,9 +93,10 @@ def eval_batch(model, batch, device, return_raw=False):
 
 class B200Adam:
     """Fused clip_grad_norm_(max_norm) + Adam (train.py:292-295,336) for a ResNetBigger with flat parameter storage: ONE kernel
-    pair (global norm, update) on the flat fp32 vector (ld_clip_adam_step, K8) instead of ~190 small PyTorch launches.
+    pair (global norm, update) on the flat fp32 vector (ld_clip_adam_step_dev, K8) instead of ~190 small PyTorch launches.
     Same arithmetic as torch.optim.Adam with default hyper-parameters; data parallel: pass world_size > 1 and the flat
-    gradient is all-reduced (mean) first."""
+    gradient is all-reduced (mean) first.  The step count lives in device memory, so a captured CUDA graph of the training
+    step replays with the right bias corrections."""
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
         self.model, self.lr, self.betas, self.eps, self.max_norm = model, lr, betas, eps, max_norm
@@ -103,7 +104,11 @@ class B200Adam:
         model._ld_fused = True
         self.exp_avg, self.exp_avg_sq = torch.zeros_like(flat), torch.zeros_like(flat)
         self.grad_norm = torch.zeros(1, device=flat.device)
-        self.steps = 0
+        self.step_d = torch.zeros(1, dtype=torch.int64, device=flat.device)
+
+    @property
+    def steps(self):
+        return int(self.step_d.item())
 
     def zero_grad(self):
         self.model.zero_flat_gradient()
@@ -117,17 +122,16 @@ class B200Adam:
         if world_size > 1:
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
             g.div_(world_size)
-        self.steps += 1
         eng = self.model._train_engine(1)
-        eng.clip_adam_step(self.model.flatten_parameters(), g, self.exp_avg, self.exp_avg_sq, self.steps, self.max_norm, self.lr,
-                           self.betas, self.eps, self.grad_norm)
+        eng.clip_adam_step_dev(self.model.flatten_parameters(), g, self.exp_avg, self.exp_avg_sq, self.step_d, self.max_norm, self.lr,
+                               self.betas, self.eps, self.grad_norm)
         self.model.mark_weights_dirty()   # the kernel wrote the parameters through raw pointers (no _version bump)
 
     def state_dict(self):
         return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "steps": self.steps}
 
     def load_state_dict(self, sd):
-        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"]); self.steps = int(sd["steps"])
+        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"]); self.step_d.fill_(int(sd["steps"]))
 
 
 def train_batch_fused(model, optimizer, batch, device, world_size=1, sync_metrics=True, gradient_accumulation_steps=1, step=1):
@@ -148,19 +152,116 @@ def train_batch_fused(model, optimizer, batch, device, world_size=1, sync_metric
     return float(loss.detach()), acc, prec, recall
 
 
-class _Stepper:
-    """Callable training step for a fixed batch shape (bench.py, Trainer): `mode` says how it launches."""
+def _metrics_vector(loss, output, labs):
+    """[loss, #correct, #correct laughs, #predicted laughs, #target laughs] on the device (no synchronisation)."""
+    preds = torch.round(output)
+    return torch.stack([loss.detach().float(), torch.sum(preds == labs).float(), torch.sum(preds * labs).float(),
+                        torch.sum(preds == 1).float(), torch.sum(labs == 1).float()])
 
-    def __init__(self, model, optimizer, device, world_size=1):
+
+def _decode_metrics(v, n):
+    loss, correct, corr_laughs, n_pred, n_trg = (float(x) for x in v)
+    prec = corr_laughs / n_pred if n_pred > 0 else 1.0
+    recall = corr_laughs / n_trg if n_trg > 0 else float('nan')   # 0/0 in the reference (train.py:222)
+    return loss, correct / n, prec, recall
+
+
+class _Stepper:
+    """Callable training step for a fixed batch shape (bench.py): forward, BCELoss, backward, (all-reduce,) fused clip + Adam and
+    the per-step loss / accuracy / precision / recall read-back of train.py:297.
+
+    The read-back is pipelined by one step -- step k's numbers are fetched while step k + 1 runs -- so the host never drains the
+    stream; `__call__` returns the metrics of the PREVIOUS step (None on the first call) and `flush()` the last one.
+    With `graph=True` the whole device side of a step (dropout masks, kernels of ld_train_forward / ld_train_backward, loss,
+    running-statistics update, NCCL all-reduce, optimiser) is captured once into a CUDA graph and replayed; the batch is copied
+    into static buffers first.  Falls back to eager launches when the capture fails (`mode` says which)."""
+
+    def __init__(self, model, optimizer, device, world_size=1, graph=True):
         self.model, self.optimizer, self.device, self.world_size = model, optimizer, device, world_size
-        self.mode = "eager (one stream, ~200 launches per step)"
+        self.want_graph, self.graph = graph, None
+        self.mode = "eager, metrics read back one step late"
+        self.pending = None
+        self.x = self.y = None
+        self.launches_per_step = None
+
+    def _body(self):
+        model = self.model
+        model.train()
+        output = model(self.x[:, None, :, :]).squeeze()
+        labs = self.y.float()
+        loss = nn.BCELoss()(output, labs)
+        loss.backward()
+        self.optimizer.step(self.world_size)
+        self.optimizer.zero_grad()
+        self.metrics_dev.copy_(_metrics_vector(loss, output.detach(), labs))
+
+    def _setup(self, batch):
+        B = batch['inputs'].shape[0]
+        self.x = torch.empty((B, 100, 44), dtype=torch.float32, device=self.device)
+        self.y = torch.empty(B, dtype=batch['is_laugh'].dtype, device=self.device)
+        self.metrics_dev = torch.zeros(5, device=self.device)
+        self.host = [torch.zeros(5).pin_memory() for _ in range(2)]
+        self.events = [torch.cuda.Event() for _ in range(2)]
+        self.k = 0
+        if not self.want_graph:
+            return
+        try:
+            eng = self.model._train_engine(B)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):   # eager warm-up on a side stream: first-use allocations, lazy module state
+                for _ in range(3):
+                    self.x.copy_(batch['inputs'], non_blocking=True); self.y.copy_(batch['is_laugh'], non_blocking=True)
+                    l0 = eng.train_kernel_launches
+                    self._body()
+                    self.launches_per_step = eng.train_kernel_launches - l0
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph = g
+            self.mode = "CUDA graph replay of the whole step, metrics read back one step late"
+        except Exception as e:   # noqa: BLE001 -- any capture problem: run eagerly, say so
+            self.graph = None
+            self.model.zero_flat_gradient()
+            torch.cuda.synchronize(self.device)
+            self.mode = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]}), metrics read back one step late"
 
     def __call__(self, batch):
-        return train_batch_fused(self.model, self.optimizer, batch, self.device, world_size=self.world_size)
+        if self.x is None or self.x.shape[0] != batch['inputs'].shape[0]:
+            self.flush()
+            self._setup(batch)
+        self.x.copy_(batch['inputs'], non_blocking=True)
+        self.y.copy_(batch['is_laugh'], non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            eng = self.model._train_engine(self.x.shape[0])
+            l0 = eng.train_kernel_launches
+            self._body()
+            self.launches_per_step = eng.train_kernel_launches - l0
+        slot = self.k & 1
+        self.host[slot].copy_(self.metrics_dev, non_blocking=True)
+        self.events[slot].record(torch.cuda.current_stream(self.device))
+        prev, self.pending = self.pending, slot
+        self.k += 1
+        if prev is None:
+            return None
+        self.events[prev].synchronize()
+        return _decode_metrics(self.host[prev].tolist(), self.x.shape[0])
+
+    def flush(self):
+        if self.pending is None:
+            return None
+        self.events[self.pending].synchronize()
+        out = _decode_metrics(self.host[self.pending].tolist(), self.x.shape[0])
+        self.pending = None
+        return out
 
 
-def make_stepper(model, optimizer, device, world_size=1):
-    return _Stepper(model, optimizer, device, world_size)
+def make_stepper(model, optimizer, device, world_size=1, graph=True):
+    return _Stepper(model, optimizer, device, world_size, graph=graph)
 
 
 def synthetic_lad_batch(batch_size, seed, device="cpu"):

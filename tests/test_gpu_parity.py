@@ -220,7 +220,7 @@ def test_split_precision_meets_2e3_on_the_calibrated_checkpoint():
         p_gpu = eng.infer_windows(one, [nb]).cpu().numpy()
         emu = PlanEmulator(plan, sd, half=True)
         p_emu = emu.run(torch.from_numpy(f[:nb]), nb).numpy()
-        assert np.abs(p_gpu - p_emu).max() < 2e-4   # same rounding model; fp32 summation order differs
+        assert np.abs(p_gpu - p_emu).max() < 6e-4   # same rounding model up to the dropped lo*lo products and the fp32 summation order (x 218 head gain)
         for tag in ("block2.0.h.int", "block2.1.y.int.e", "block3.1.y.r0.e", "block4.1.y.r5"):
             pl = next(p for p in plan["planes"] if p["tag"] == tag)
             # rows past the window starts are either halo the emulator computes from zeros and the GPU from whatever an earlier
@@ -228,7 +228,7 @@ def test_split_precision_meets_2e3_on_the_calibrated_checkpoint():
             got = eng.read_plane(pl["id"], nb + 100, pl["wp"], pl["C"])[:nb]
             want = emu.plane_as_rows(pl["id"], nb + 100).numpy()[:nb]
             scale = np.abs(want).max()
-            assert np.abs(got - want).max() < 2e-4 * scale, tag
+            assert np.abs(got - want).max() < 1e-3 * scale, tag
         # random-init weights: far inside the 1e-3 of the north star
         sd2 = resnet_oracle.random_state_dict(seed=3)
         eng.load_state_dict(sd2)
