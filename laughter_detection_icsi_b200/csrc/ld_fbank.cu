@@ -102,7 +102,7 @@ fbank_kernel(const int16_t* __restrict__ pcm, long long n_samples, long long n_f
     const int F = mel.n_filters;
     for (int i = tid; i < F; i += 256) { S.mel_lo[i] = mel.lo[i]; S.mel_len[i] = mel.len[i]; S.mel_off[i] = mel.off[i]; }
     {
-        const int total_w = mel.off[F - 1] + mel.len[F - 1];
+        const int total_w = mel.off[F - 1] + 4 * mel.len[F - 1];   // run lengths are in 4-bin vectors
         for (int i = tid; i < total_w; i += 256) S.melw[i] = mel.weights[i];
     }
     // inter-pass twiddles W256^(t * k1): fixed per thread, kept in registers

@@ -29,10 +29,11 @@ __device__ __forceinline__ int find_channel(const ChannelTable& ct, long long s,
     return (local >= 0 && local < ct.frames[lo]) ? lo : -1;
 }
 
-// One thread computes kStemPx consecutive pixels of one GLOBAL feature row for all 64 channels, keeping the three kernel-row
-// partial sums s_ky apart: every stem plane (interior: s0 + s1 + s2; top edge of a window: s1 + s2; bottom edge: s0 + s1 at
-// row + 99) is a masked sum of them, so the 3 x 3 taps are multiplied once for all planes instead of once per plane
-// (9 instead of 21 multiply-adds per pixel and channel), and the feature patch is read once.
+// One warp computes 32 * kStemPx consecutive pixels of the flattened (global feature row, padded column) index space for all
+// 64 channels: lane l owns pixels base + l + 32 i, so every 16-byte store instruction of the warp covers 512 contiguous
+// bytes of a plane.  The three kernel-row partial sums s_ky stay apart: every stem plane (interior: s0 + s1 + s2; top edge
+// of a window: s1 + s2; bottom edge: s0 + s1, 99 rows up) is a masked sum of them, so the 3 x 3 taps are multiplied once
+// for all planes (9 instead of 21 multiply-adds per pixel and channel) and the feature patch is read once.
 constexpr int kStemPx = 4;
 __global__ void __launch_bounds__(256)
 stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long long chunk_row0, int rows, int row_lo, int rows_total) {
@@ -43,32 +44,40 @@ stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long
     __syncthreads();
 
     const int wp = L.W + 2;
-    const int groups_per_row = (wp + kStemPx - 1) / kStemPx;
-    const long long gi = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (gi >= static_cast<long long>(rows_total) * groups_per_row) return;
-    const int rr = static_cast<int>(gi / groups_per_row);
-    const int G = row_lo + rr;                                              // chunk-relative global row of the centre tap
-    const int pc0 = static_cast<int>(gi - static_cast<long long>(rr) * groups_per_row) * kStemPx;   // first padded column
+    const long long n_pix = static_cast<long long>(rows_total) * wp;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long base = warp * (32 * kStemPx);
+    if (base >= n_pix) return;
 
-    // the 3 x (kStemPx + 2) input patch; real column = padded column - 1
-    float x[3][kStemPx + 2];
+    // per pixel: the 3 x 3 feature patch (real column = padded column - 1) and where it lands in each plane
+    float x[kStemPx][3][3];
+    long long dst[kStemPx][kMaxStemJobs];   // element offset of the pixel inside plane j, or -1
+    bool pad[kStemPx];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        long long local = 0;
-        const int c = find_channel(ct, chunk_row0 + G + ky - 1, local);
-        const float* frow = (c >= 0) ? feats + (ct.feat_off[c] + local) * L.W : nullptr;
+    for (int i = 0; i < kStemPx; ++i) {
+        const long long p = base + lane + 32 * i;
+        const bool live = p < n_pix;
+        const int rr = live ? static_cast<int>(p / wp) : 0;
+        const int pc = live ? static_cast<int>(p - static_cast<long long>(rr) * wp) : 0;
+        const int G = row_lo + rr;                       // chunk-relative global row of the centre tap
+        pad[i] = pc == 0 || pc == wp - 1;
 #pragma unroll
-        for (int k = 0; k < kStemPx + 2; ++k) {
-            const int cc = pc0 - 1 + k - 1;
-            x[ky][k] = (frow != nullptr && cc >= 0 && cc < L.W) ? __ldg(frow + cc) : 0.f;
+        for (int ky = 0; ky < 3; ++ky) {
+            long long local = 0;
+            const int c = live ? find_channel(ct, chunk_row0 + G + ky - 1, local) : -1;
+            const float* frow = (c >= 0) ? feats + (ct.feat_off[c] + local) * L.W : nullptr;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int cc = pc - 1 + kx - 1;
+                x[i][ky][kx] = (frow != nullptr && cc >= 0 && cc < L.W) ? __ldg(frow + cc) : 0.f;
+            }
         }
-    }
-    // plane row this global row lands on, per job (row = G - row_shift), or -1
-    int prow[kMaxStemJobs];
 #pragma unroll
-    for (int j = 0; j < kMaxStemJobs; ++j) {
-        const int r = G - (j < L.n_jobs ? L.jobs[j].row_shift : 0);
-        prow[j] = (j < L.n_jobs && r >= 0 && r < rows) ? r : -1;
+        for (int j = 0; j < kMaxStemJobs; ++j) {
+            const int r = G - (j < L.n_jobs ? L.jobs[j].row_shift : 0);
+            dst[i][j] = (live && j < L.n_jobs && r >= 0 && r < rows) ? (static_cast<long long>(r) * wp + pc) * 8 : -1;
+        }
     }
     for (int kc = 0; kc < 8; ++kc) {
         float part[3][kStemPx][8];
@@ -79,39 +88,36 @@ stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long
 #pragma unroll
             for (int t = 0; t < 9; ++t) w[t] = s_w[ch * 9 + t];
 #pragma unroll
-            for (int px = 0; px < kStemPx; ++px)
+            for (int i = 0; i < kStemPx; ++i)
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
                     float a = 0.f;
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) a = fmaf(w[ky * 3 + kx], x[ky][px + kx], a);
-                    part[ky][px][e] = a;
+                    for (int kx = 0; kx < 3; ++kx) a = fmaf(w[ky * 3 + kx], x[i][ky][kx], a);
+                    part[ky][i][e] = a;
                 }
         }
 #pragma unroll
         for (int j = 0; j < kMaxStemJobs; ++j) {
-            if (prow[j] < 0) continue;
+            if (j >= L.n_jobs) continue;
             const StemJob job = L.jobs[j];
 #pragma unroll
-            for (int px = 0; px < kStemPx; ++px) {
-                const int pc = pc0 + px;
-                if (pc >= wp) continue;
-                const bool pad = pc == 0 || pc == wp - 1;
+            for (int i = 0; i < kStemPx; ++i) {
+                if (dst[i][j] < 0) continue;
                 float o[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    // same order of additions as a per-plane evaluation: ky ascending over the rows the plane sees
-                    float a = 0.f;
+                    float a = 0.f;   // ky ascending over the kernel rows the plane sees
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
-                        if ((job.mask >> ky) & 1) a += part[ky][px][e];
+                        if ((job.mask >> ky) & 1) a += part[ky][i][e];
                     o[e] = fmaxf(fmaf(a, s_scale[kc * 8 + e], s_shift[kc * 8 + e]), 0.f);
                 }
                 uint4 ov;
                 __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) oh[e] = pad ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(o[2 * e], o[2 * e + 1]);
-                *reinterpret_cast<uint4*>(job.out + (static_cast<long long>(prow[j]) * wp + pc) * 8 + kc * job.kc_stride) = ov;
+                for (int e = 0; e < 4; ++e) oh[e] = pad[i] ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(o[2 * e], o[2 * e + 1]);
+                *reinterpret_cast<uint4*>(job.out + dst[i][j] + kc * job.kc_stride) = ov;
             }
         }
     }
@@ -183,8 +189,8 @@ cudaError_t launch_stem(const StemLaunch& L, const ChannelTable& ct, const float
     int lo = 0, hi = 0;
     for (int j = 0; j < L.n_jobs; ++j) { lo = j == 0 ? L.jobs[j].row_shift : (L.jobs[j].row_shift < lo ? L.jobs[j].row_shift : lo); hi = L.jobs[j].row_shift > hi ? L.jobs[j].row_shift : hi; }
     const int rows_total = rows + hi - lo;
-    const long long groups = static_cast<long long>(rows_total) * ((L.W + 2 + kStemPx - 1) / kStemPx);
-    stem_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, stream>>>(L, ct, feats, chunk_row0, rows, lo, rows_total);
+    const long long threads = (static_cast<long long>(rows_total) * (L.W + 2) + kStemPx - 1) / kStemPx;   // 32 * kStemPx pixels per warp
+    stem_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(L, ct, feats, chunk_row0, rows, lo, rows_total);
     return cudaGetLastError();
 }
 
