@@ -108,6 +108,15 @@ LD_API int ld_resnet_load_weights(ld_ctx* ctx, const ld_tensor* tensors, int32_t
 LD_API int ld_resnet_infer_windows(ld_ctx* ctx, const float* feats_d, const int64_t* chan_frames, int32_t n_chan,
                             float* probs_d, void* stream);
 
+/* LAD window gather (training input).  Replaces the reference's cut construction row_track.truncate(offset=sub_start,
+ * duration=sub_duration).pad(duration=1.0) (compute_features.py:167) + PrecomputedFeatures()(cuts) (datasets.py:56): builds
+ * out_d fp32 (n_windows, num_frames, num_filters) from whole-track features resident on the device.
+ * tracks_d: fp32 (sum_t T_t, num_filters), tracks laid end to end; track_off_d / track_len_d: int64 [n_tracks] first row and
+ * rows of each track; triples_d: int32 [n_windows][3] = (track, first frame, frames taken); rows past `frames` or past the
+ * end of the track are filled with pad_value (Lhotse's LOG_EPSILON for log-domain features). */
+LD_API int ld_gather_windows(ld_ctx* ctx, const float* tracks_d, const int64_t* track_off_d, const int64_t* track_len_d,
+                      const int32_t* triples_d, int32_t n_windows, float pad_value, float* out_d, void* stream);
+
 /* K4. Replaces the run detection of laugh_segmenter.get_laughter_instances (laugh_segmenter.py:87-105)
  * for n_thr thresholds at once: maximal runs of fix_over_underflow(p) > thr inside each channel, as
  * (first_frame, last_frame) pairs relative to the channel start.  prob_is_f64: probs_d holds doubles.

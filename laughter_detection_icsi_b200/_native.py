@@ -54,6 +54,7 @@ SIGNATURES = {
     "ld_fbank_reset_mel": (c_int, [c_void_p]),
     "ld_resnet_load_weights": (c_int, [c_void_p, POINTER(LdTensor), c_int32]),
     "ld_resnet_infer_windows": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_void_p]),
+    "ld_gather_windows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, ctypes.c_float, c_void_p, c_void_p]),
     "ld_segment_runs": (c_int, [c_void_p, c_void_p, c_int32, POINTER(c_int64), c_int32, POINTER(c_double), POINTER(c_double),
                                 c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "ld_filter_min_length": (c_int64, [POINTER(c_int32), POINTER(c_int32), c_int64, c_double, c_double,

@@ -94,6 +94,52 @@ class FeatureStore:
         return FeatureCut(window, int(label), cut_id or f"{meeting_id}_{chan_id}_{first}")
 
 
+class GpuCutSampler:
+    """LAD cuts as index triples over whole-track features that stay in HBM: the batch tensor
+    is gathered on the GPU by ld_gather_windows, so training reads no features from the host.  Same frame arithmetic as
+    FeatureStore.cut (truncate(sub_start, sub_duration).pad(1 s) on the 10 ms grid, LOG_EPSILON padding)."""
+
+    def __init__(self, store, device=0):
+        self.engine = _engine.get_engine(device)
+        dev = self.engine.device
+        self.keys = list(store.tracks)
+        self.index = {k: i for i, k in enumerate(self.keys)}
+        lens = [store.tracks[k].shape[0] for k in self.keys]
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64) if lens else np.zeros(0, dtype=np.int64)
+        self.track_len_host = np.asarray(lens, dtype=np.int64)
+        self.tracks = torch.from_numpy(np.concatenate([store.tracks[k] for k in self.keys]).astype(np.float32)).to(dev)
+        self.track_off = torch.from_numpy(offs).to(dev)
+        self.track_len = torch.from_numpy(self.track_len_host).to(dev)
+
+    def triples(self, rows, min_seg_duration=1.0, shuffle_seed=None):
+        """(int32 (n, 3) triples, int32 (n,) labels) for data-frame rows, shuffled like cuts_from_dataframe."""
+        n_target = _round_half_up(min_seg_duration / FRAME_SHIFT)
+        tri = np.zeros((len(rows), 3), dtype=np.int32)
+        lab = np.zeros(len(rows), dtype=np.int32)
+        for i, r in enumerate(rows):
+            t = self.index[FeatureStore.key(r["meeting_id"], r["chan_id"])]
+            first = _round_half_up(float(r["sub_start"]) / FRAME_SHIFT)
+            n = min(_round_half_up(min(float(r["sub_duration"]), min_seg_duration) / FRAME_SHIFT), n_target)
+            first = max(0, min(first, int(self.track_len_host[t])))
+            tri[i] = (t, first, n)
+            lab[i] = int(r["label"])
+        if shuffle_seed is not None:
+            order = np.random.default_rng(shuffle_seed).permutation(len(rows))
+            tri, lab = tri[order], lab[order]
+        return tri, lab
+
+    def batches(self, tri, lab, max_cuts=32):
+        """LadDataset-shaped batches whose 'inputs' are CUDA tensors gathered on the device."""
+        dev = self.engine.device
+        tri_d = torch.from_numpy(np.ascontiguousarray(tri)).to(dev)
+        lab_d = torch.from_numpy(np.ascontiguousarray(lab)).to(dev)
+        for i in range(0, len(tri), max_cuts):
+            t = tri_d[i:i + max_cuts].contiguous()
+            inputs = self.engine.gather_windows(self.tracks, self.track_off, self.track_len, t, LOG_EPSILON)
+            yield {"inputs": inputs, "input_lens": torch.full((t.shape[0],), cfg.FEAT['num_samples'], dtype=torch.int32),
+                   "is_laugh": lab_d[i:i + max_cuts], "cut": None}
+
+
 def read_data_df(path):
     """Rows of a `{split}_df.csv` (create_data_df.py; columns start,duration,sub_start,sub_duration,audio_path,meeting_id,
     chan_id,label) as dicts."""

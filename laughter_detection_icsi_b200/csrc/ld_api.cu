@@ -726,6 +726,18 @@ int ld_fbank_reset_mel(ld_ctx* ctx) {
     return LD_OK;
 }
 
+int ld_gather_windows(ld_ctx* ctx, const float* tracks_d, const int64_t* track_off_d, const int64_t* track_len_d, const int32_t* triples_d,
+                      int32_t n_windows, float pad_value, float* out_d, void* stream_v) {
+    if (!ctx || !tracks_d || !track_off_d || !track_len_d || !triples_d || !out_d || n_windows < 0) return fail(LD_ERR_INVALID, "bad arguments");
+    LD_CUDA(cudaSetDevice(ctx->device));
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset type");
+    ++ctx->launches;
+    LD_CUDA(ld::launch_gather_windows(tracks_d, reinterpret_cast<const long long*>(track_off_d), reinterpret_cast<const long long*>(track_len_d),
+                                      triples_d, n_windows, ctx->cfg.num_frames, ctx->cfg.num_filters, pad_value, out_d,
+                                      static_cast<cudaStream_t>(stream_v)));
+    return LD_OK;
+}
+
 int ld_segment_runs(ld_ctx* ctx, const void* probs_d, int32_t prob_is_f64, const int64_t* chan_frames, int32_t n_chan,
                     const double* thr_cmp, const double* thr_raw, int32_t n_thr, int32_t* starts_d, int32_t* ends_d,
                     int32_t* chan_d, int32_t* counts_d, int32_t cap, void* stream_v) {

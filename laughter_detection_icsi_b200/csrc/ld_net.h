@@ -105,4 +105,8 @@ cudaError_t launch_filtfilt(const void* probs, int is_f64, long long n, const do
                             double* scratch, cudaStream_t stream);
 size_t filtfilt_scratch_doubles(long long n);
 
+// ld_gather.cu
+cudaError_t launch_gather_windows(const float* feats, const long long* track_off, const long long* track_len, const int* triples,
+                                  int n_windows, int n_frames, int F, float pad_value, float* out, cudaStream_t stream);
+
 }  // namespace ld

@@ -244,6 +244,26 @@ class Engine:
                                                out.data_ptr(), self._stream()))
         return out
 
+    # ------------------------------------------------------------------------------------------ LAD window gather
+    def gather_windows(self, tracks, track_off, track_len, triples, pad_value):
+        """(B, num_frames, num_filters) float32 CUDA batch of LAD windows from device-resident whole-track features.
+        tracks: (sum T, F) float32 CUDA; track_off / track_len: int64 CUDA [n_tracks]; triples: int32 CUDA (B, 3) =
+        (track, first frame, frames taken)."""
+        if not (tracks.is_cuda and tracks.dtype == torch.float32 and tracks.is_contiguous() and tracks.dim() == 2
+                and tracks.shape[1] == self.cfg.num_filters):
+            raise ValueError("tracks must be a contiguous float32 CUDA tensor (sum T, num_filters)")
+        for t, dt in ((track_off, torch.int64), (track_len, torch.int64), (triples, torch.int32)):
+            if not (t.is_cuda and t.dtype == dt and t.is_contiguous()):
+                raise ValueError("track tables must be int64 and triples int32 contiguous CUDA tensors")
+        if triples.dim() != 2 or triples.shape[1] != 3 or track_off.numel() != track_len.numel():
+            raise ValueError("triples must be (B, 3); track_off and track_len must have one entry per track")
+        B = triples.shape[0]
+        out = torch.empty((B, self.cfg.num_frames, self.cfg.num_filters), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.ld_gather_windows(self._h, tracks.data_ptr(), track_off.data_ptr(), track_len.data_ptr(), triples.data_ptr(), B,
+                                             float(pad_value), out.data_ptr(), self._stream()))
+        return out
+
     # ------------------------------------------------------------------------------------------ training
     def train_create(self, max_batch=256):
         """Allocates the dense training network (bf16 operands) for batches of up to max_batch windows."""

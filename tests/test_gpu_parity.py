@@ -469,6 +469,39 @@ def test_segment_laughter_cli_end_to_end(tmp_path):
                                "--output_dir", str(out)])
 
 
+def test_gpu_cut_sampler_matches_host_cuts():
+    """LAD windows gathered on the GPU from device-resident whole-track features
+    (ld_gather_windows) are bit-identical to the host-side truncate + pad cuts (compute_features.py:167 of the reference),
+    incl. short cuts, cuts that run off the end of a track and several tracks."""
+    from laughter_detection_icsi_b200 import compute_features as cf
+    rng = np.random.default_rng(0)
+    store = cf.FeatureStore()
+    store.add_features("Bmr001", "chan0", rng.normal(-5, 3, (3000, 44)).astype(np.float32), "a.sph", 30.0)
+    store.add_features("Bmr001", "chan1", rng.normal(-5, 3, (1234, 44)).astype(np.float32), "b.sph", 12.34)
+    store.add_features("Bed002", "chan3", rng.normal(-5, 3, (100, 44)).astype(np.float32), "c.sph", 1.0)
+    rows = []
+    for i in range(70):
+        m, c, T = [("Bmr001", "chan0", 30.0), ("Bmr001", "chan1", 12.34), ("Bed002", "chan3", 1.0)][i % 3]
+        rows.append({"meeting_id": m, "chan_id": c, "sub_start": float(rng.uniform(0, T)), "sub_duration": float(rng.choice([0.2, 0.37, 1.0, 1.5])),
+                     "label": int(i % 2)})
+    rows.append({"meeting_id": "Bmr001", "chan_id": "chan1", "sub_start": 12.34, "sub_duration": 1.0, "label": 1})   # starts at the very end
+    host_cuts = cf.cuts_from_dataframe(rows, store, shuffle_seed=3)
+    sampler = cf.GpuCutSampler(store)
+    tri, lab = sampler.triples(rows, shuffle_seed=3)
+    got = list(sampler.batches(tri, lab))
+    want = list(cf.training_batches(host_cuts))
+    assert [b["inputs"].shape[0] for b in got] == [32, 32, 7]
+    for g, w in zip(got, want):
+        assert g["inputs"].is_cuda and torch.equal(g["inputs"].cpu(), w["inputs"]) and torch.equal(g["is_laugh"].cpu(), w["is_laugh"])
+    # and the batch trains
+    from laughter_detection_icsi_b200 import train as ld_train
+    m = models.ResNetBigger(dropout_rate=0.5, linear_layer_size=48, filter_sizes=[64, 32, 16, 16])
+    m.load_state_dict(synth.synthetic_state_dict(head_gain=1.0, head_bias_shift=0.0))
+    m.set_device("cuda")
+    loss = ld_train.train_batch(m, torch.optim.Adam(m.parameters()), got[0], torch.device("cuda"))[0]
+    assert np.isfinite(loss)
+
+
 def test_feature_store_from_wav_feeds_training(tmp_path):
     """whole-track features from K1 -> LAD cuts from a data frame -> LadDataset batch ->
     one training step on the B200 kernels."""
