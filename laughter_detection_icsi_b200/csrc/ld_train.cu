@@ -282,6 +282,8 @@ bn_apply_kernel(TPlane z, BnRef bn, int relu, int res_mode, TPlane res, BnRef bn
 
 // ------------------------------------------------------------------------------------------------ BatchNorm backward
 // g = dy * [y > 0] (relu) ; reductions sum g, sum g*xhat per channel.
+// relu = 2: y = relu(bn(z)) without a residual, so [y > 0] = [z * ya + yb > 0] is recomputed from z with the very expression the
+// forward pass evaluated (bn_apply_kernel) and the y plane is not read at all.
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, int B, float* __restrict__ sums /*[2C]*/) {
     __shared__ float s_acc[128];
@@ -292,9 +294,12 @@ bn_bwd_reduce_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, int B, f
     __syncthreads();
     const EwWalk w(C / 8, B, z.H, z.W);
     const int kc = w.kc;
-    float xa[8], xb[8], sg[8], sx[8];
+    float xa[8], xb[8], ya[8], yb[8], sg[8], sx[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { xa[e] = s.xa[kc * 8 + e]; xb[e] = s.xb[kc * 8 + e]; sg[e] = 0.f; sx[e] = 0.f; }
+    for (int e = 0; e < 8; ++e) {
+        xa[e] = s.xa[kc * 8 + e]; xb[e] = s.xb[kc * 8 + e]; ya[e] = s.ya[kc * 8 + e]; yb[e] = s.yb[kc * 8 + e];
+        sg[e] = 0.f; sx[e] = 0.f;
+    }
     for (unsigned g = w.group; g < w.n_groups; g += w.group_stride) {
         int b, r0, c0, which;
         if (!w.pixel(g, b, r0, c0)) continue;
@@ -302,11 +307,12 @@ bn_bwd_reduce_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, int B, f
         const long long pz = plain_off(z, b, r0, c0);   // dy and y share one geometry (plain like z, or quad)
         const long long pd = any_off(dy, b, r0, c0, pz, which);
         load8(dy.base[which] + kc * dy.kc_stride + pd, gg);
-        if (relu) load8(y.base[which] + kc * y.kc_stride + pd, yy);
+        if (relu == 1) load8(y.base[which] + kc * y.kc_stride + pd, yy);
         load8(z.base[0] + kc * z.kc_stride + pz, zz);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float ge = (relu && !(yy[e] > 0.f)) ? 0.f : gg[e];
+            const bool off = relu == 1 ? !(yy[e] > 0.f) : (relu == 2 ? !(fmaf(zz[e], ya[e], yb[e]) > 0.f) : false);
+            const float ge = off ? 0.f : gg[e];
             sg[e] += ge;
             sx[e] = fmaf(ge, fmaf(zz[e], xa[e], xb[e]), sx[e]);
         }
@@ -345,11 +351,11 @@ bn_bwd_apply_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, const flo
     __syncthreads();
     const EwWalk w(C / 8, B, z.H, z.W);
     const int kc = w.kc;
-    float xa[8], xb[8], ya[8], c1[8], c2[8];   // c1 = mean(g), c2 = mean(g xhat)
+    float xa[8], xb[8], ya[8], yb[8], c1[8], c2[8];   // c1 = mean(g), c2 = mean(g xhat)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int c = kc * 8 + e;
-        xa[e] = s.xa[c]; xb[e] = s.xb[c]; ya[e] = s.ya[c];
+        xa[e] = s.xa[c]; xb[e] = s.xb[c]; ya[e] = s.ya[c]; yb[e] = s.yb[c];
         c1[e] = sums[c] * bn.inv_n; c2[e] = sums[C + c] * bn.inv_n;
     }
     for (unsigned g = w.group; g < w.n_groups; g += w.group_stride) {
@@ -359,11 +365,12 @@ bn_bwd_apply_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, const flo
         const long long pz = plain_off(z, b, r0, c0);   // dy and y share one geometry (plain like z, or quad); dz, g_out are plain
         const long long pd = any_off(dy, b, r0, c0, pz, which);
         load8(dy.base[which] + kc * dy.kc_stride + pd, gg);
-        if (relu) load8(y.base[which] + kc * y.kc_stride + pd, yy);
+        if (relu == 1) load8(y.base[which] + kc * y.kc_stride + pd, yy);
         load8(z.base[0] + kc * z.kc_stride + pz, zz);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            if (relu && !(yy[e] > 0.f)) gg[e] = 0.f;
+            if (relu == 1 && !(yy[e] > 0.f)) gg[e] = 0.f;
+            if (relu == 2 && !(fmaf(zz[e], ya[e], yb[e]) > 0.f)) gg[e] = 0.f;   // [y > 0] recomputed from z (no residual)
             const float xh = fmaf(zz[e], xa[e], xb[e]);
             o[e] = ya[e] * (gg[e] - c1[e] - xh * c2[e]);
         }
@@ -1421,7 +1428,7 @@ cudaError_t train_backward(TrainNet* n, const float* dprobs, float* grads, cudaS
         bn_backward(dout, out, 1, c2, 1, blk.g);
         if (cudaError_t e = run_wgrad(n, c2, grads + c2.w_off, stream)) { err = "wgrad " + c2.name; return e; }
         if (cudaError_t e = run_gemm(n, c2.bwd, blk.dh, stream, err)) return e;
-        bn_backward(blk.dh, h, 1, c1, 0, blk.g);
+        bn_backward(blk.dh, h, 2, c1, 0, blk.g);   // h = relu(bn1(z1)): the mask comes from z1, h is not read
         if (cudaError_t e = run_wgrad(n, c1, grads + c1.w_off, stream)) { err = "wgrad " + c1.name; return e; }
         if (blk.sc >= 0) {
             ConvHost& cs = n->convs[blk.sc];
@@ -1433,7 +1440,7 @@ cudaError_t train_backward(TrainNet* n, const float* dprobs, float* grads, cudaS
     }
     {   // stem
         ConvHost& c = n->convs[0];
-        bn_backward(n->dlevels[0], n->levels[0], 1, c, 0, c.dz);
+        bn_backward(n->dlevels[0], n->levels[0], 2, c, 0, c.dz);
         stem_wgrad_kernel<<<n->num_sms * 4, 256, 0, stream>>>(n->x_d, B, n->cfg.H, n->cfg.W, c.dz, grads + c.w_off);
         ++n->launches;
     }
