@@ -641,10 +641,13 @@ def run_cli(args):
         argv = ["--config", "resnet_base", "--model_path", os.path.join(tmp, "ck"), "--input_audio_file", wav, "--thresholds",
                 ",".join(str(t) for t in synth.eval_grid()[0]), "--min_lengths", "0.0,0.1,0.2", "--save_to_textgrid", "True",
                 "--save_to_audio_files", "False", "--output_dir", os.path.join(tmp, "out")]
+        import contextlib
+        import io
         times = []
         for _ in range(max(args.warmup, 1) + args.steps):
             t0 = time.perf_counter()
-            segment_laughter.main(argv)
+            with contextlib.redirect_stdout(io.StringIO()):   # the CLI prints one line per setting; stdout carries ONE JSON line
+                segment_laughter.main(argv)
             torch.cuda.synchronize()
             times.append(time.perf_counter() - t0)
         gpu_s = statistics.median(times[max(args.warmup, 1):])

@@ -10,6 +10,8 @@
 // A "sequence" is the concatenation of channels with zero gaps; seq rows that fall into a gap or past
 // the end read as all-zero features, which is exactly InferenceDataset's right zero padding
 // (reference datasets.py:85-93).
+#include <cstdlib>
+
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -34,7 +36,7 @@ __device__ __forceinline__ int find_channel(const ChannelTable& ct, long long s,
 // bytes of a plane.  The three kernel-row partial sums s_ky stay apart: every stem plane (interior: s0 + s1 + s2; top edge
 // of a window: s1 + s2; bottom edge: s0 + s1, 99 rows up) is a masked sum of them, so the 3 x 3 taps are multiplied once
 // for all planes (9 instead of 21 multiply-adds per pixel and channel) and the feature patch is read once.
-constexpr int kStemPx = 4;
+template <int kStemPx>
 __global__ void __launch_bounds__(256)
 stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long long chunk_row0, int rows, int row_lo, int rows_total) {
     __shared__ float s_w[64 * 9];
@@ -189,8 +191,12 @@ cudaError_t launch_stem(const StemLaunch& L, const ChannelTable& ct, const float
     int lo = 0, hi = 0;
     for (int j = 0; j < L.n_jobs; ++j) { lo = j == 0 ? L.jobs[j].row_shift : (L.jobs[j].row_shift < lo ? L.jobs[j].row_shift : lo); hi = L.jobs[j].row_shift > hi ? L.jobs[j].row_shift : hi; }
     const int rows_total = rows + hi - lo;
-    const long long threads = (static_cast<long long>(rows_total) * (L.W + 2) + kStemPx - 1) / kStemPx;   // 32 * kStemPx pixels per warp
-    stem_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(L, ct, feats, chunk_row0, rows, lo, rows_total);
+    // pixels per thread: 2 keeps the kernel under 128 registers (two CTAs per SM), 4 reuses every weight fetch twice as often
+    static const int px = []() { const char* v = std::getenv("LD_STEM_PX"); return (v && std::atoi(v) == 4) ? 4 : 2; }();
+    const long long threads = (static_cast<long long>(rows_total) * (L.W + 2) + px - 1) / px;   // 32 * px pixels per warp
+    const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
+    if (px == 4) stem_kernel<4><<<grid, 256, 0, stream>>>(L, ct, feats, chunk_row0, rows, lo, rows_total);
+    else stem_kernel<2><<<grid, 256, 0, stream>>>(L, ct, feats, chunk_row0, rows, lo, rows_total);
     return cudaGetLastError();
 }
 
