@@ -65,7 +65,8 @@ __host__ __device__ inline GemmSmem gemm_smem_layout(int cin, int cout, int n_wt
     s.stage_off = (s.jobs_off + static_cast<uint32_t>(n_jobs) * static_cast<uint32_t>(sizeof(GemmJob)) + 127u) & ~127u;
     s.stage_bytes = static_cast<uint32_t>(ext_alloc) * 16u * (cin / 8) * groups_per_stage;
     s.param_off = s.stage_off + n_stages * s.stage_bytes;
-    s.bar_off = s.param_off + 2u * static_cast<uint32_t>((cout + 31) / 32 * 32) * sizeof(float);
+    // shift[cout] (mode 0) / channel sums [2][..] + BatchNorm coefficients xa, xb, ya, yb [4][..] (mode 1)
+    s.bar_off = s.param_off + 6u * static_cast<uint32_t>((cout + 31) / 32 * 32) * sizeof(float);
     s.bar_off = (s.bar_off + 15u) & ~15u;
     s.total = s.bar_off + (2 * kMaxStages + 2 * kAccStages + 1 + kIssuers) * 8 + 16;
     return s;
@@ -346,6 +347,24 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
             return inner;
         };
         mbar_wait(bar_w, 0);   // the job table is in shared memory
+        const bool bwd_stats = MODE == 1 && L.stats != nullptr && L.stats_kind == 1;
+        float* s_coef = s_shift + 2 * kStatAll;   // xa | xb | ya | yb, kStatAll floats each (mode 1, backward statistics)
+        if constexpr (MODE == 1) {
+            if (bwd_stats && lane < CH) {
+                // the same expressions as bn_coef_setup (ld_train.cu): the ReLU mask recomputed from z must match the forward pass.
+                // Every warp of a channel half writes identical values (after griddep_wait: the sums come from earlier kernels).
+                const int c = half * CH + lane;
+                const float m = L.bwd.fwd_sums[c] * L.bwd.inv_n;
+                const float var = fmaxf(L.bwd.fwd_sums[COUT + c] * L.bwd.inv_n - m * m, 0.f);
+                const float inv = rsqrtf(var + 1e-5f);
+                const float gam = L.bwd.gamma[c];
+                s_coef[c] = inv;
+                s_coef[kStatAll + c] = -m * inv;
+                s_coef[2 * kStatAll + c] = gam * inv;
+                s_coef[3 * kStatAll + c] = fmaf(-m * inv, gam, L.bwd.beta[c]);
+            }
+            __syncwarp();
+        }
         TileWalk tw(blockIdx.x, gridDim.x, n_jobs);
         for (int it = 0; it < my_tiles; ++it) {
             const GemmJob& job = s_jobs[tw.job];
@@ -369,6 +388,24 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
             const int n_outs = job.n_outs;
             tw.next();
 
+            // backward statistics: this pixel's z (and y) values are fetched while the MMAs of the tile still run
+            uint4 zr[CH / 8], yr[CH / 8];
+            if constexpr (MODE == 1) {
+                if (bwd_stats) {
+                    const bool real_px = valid && inner;
+#pragma unroll
+                    for (int kc = 0; kc < CH / 8; ++kc) {
+                        zr[kc] = yr[kc] = make_uint4(0u, 0u, 0u, 0u);
+                        if (real_px) {
+                            zr[kc] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(L.bwd.z) +
+                                                                     (half * (CH / 8) + kc) * L.bwd.z_kc + static_cast<long long>(p) * 8);
+                            if (L.bwd.mask_mode == 1)
+                                yr[kc] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(L.bwd.y) +
+                                                                         (half * (CH / 8) + kc) * L.bwd.y_kc + static_cast<long long>(p) * 8);
+                        }
+                    }
+                }
+            }
             long long t0 = profiling ? clock64() : 0;
             mbar_wait(bar_acc_full + 8 * acc, acc_phase);
             if (profiling) { const long long t1 = clock64(); c_wait += t1 - t0; t0 = t1; }
@@ -447,10 +484,30 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
                     }
                     if (L.stats != nullptr) {   // BatchNorm batch statistics from the fp32 accumulators
                         float a[kStatN], b[kStatN];
+                        if (bwd_stats) {   // backward: sum g, sum g * xhat with g = dy * [y > 0]
+                            const int mask_mode = L.bwd.mask_mode;
 #pragma unroll
-                        for (int c = 0; c < kStatN; ++c) {
-                            const float z = (c < CH && real) ? __uint_as_float(v[c < CH ? c : 0]) : 0.f;
-                            a[c] = z; b[c] = z * z;
+                            for (int c = 0; c < kStatN; ++c) {
+                                float g = 0.f, gx = 0.f;
+                                if (c < CH && real) {
+                                    const __nv_bfloat16* zh = reinterpret_cast<const __nv_bfloat16*>(&zr[(c < CH ? c : 0) / 8]);
+                                    const __nv_bfloat16* yh = reinterpret_cast<const __nv_bfloat16*>(&yr[(c < CH ? c : 0) / 8]);
+                                    const float zf = __bfloat162float(zh[c % 8]);
+                                    const int cc = half * CH + c;
+                                    bool on = true;
+                                    if (mask_mode == 1) on = __bfloat162float(yh[c % 8]) > 0.f;
+                                    if (mask_mode == 2) on = fmaf(zf, s_coef[2 * kStatAll + cc], s_coef[3 * kStatAll + cc]) > 0.f;
+                                    g = on ? __uint_as_float(v[c < CH ? c : 0]) : 0.f;
+                                    gx = g * fmaf(zf, s_coef[cc], s_coef[kStatAll + cc]);
+                                }
+                                a[c] = g; b[c] = gx;
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < kStatN; ++c) {
+                                const float z = (c < CH && real) ? __uint_as_float(v[c < CH ? c : 0]) : 0.f;
+                                a[c] = z; b[c] = z * z;
+                            }
                         }
                         warp_reduce_channels<kStatN>(a, lane);
                         warp_reduce_channels<kStatN>(b, lane);

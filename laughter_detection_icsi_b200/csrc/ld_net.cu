@@ -125,14 +125,18 @@ stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long
     }
 }
 
-__global__ void __launch_bounds__(128)
+// 128 windows per CTA, 384 threads: thread (g, w) first pools group g (4 rows x 4 columns) of window w -- its 4 x 2 x 4 (x 2 in
+// split precision) 16-byte loads are independent and all in flight together -- into shared memory, then threads 0..127 run the
+// dense part of one window each.  (One thread per window walking its 96 loads in sequence left the kernel latency-bound.)
+constexpr int kHeadWin = 128;
+__global__ void __launch_bounds__(3 * kHeadWin)
 head_kernel(HeadLaunch L, ChannelTable ct, float* __restrict__ probs, long long chunk_row0, int nb) {
     extern __shared__ float s_par[];
-    // layout: bn2 scale[F] shift[F] | W1[32*F] b1[32] | bn3 scale[32] shift[32] | w2[32] b2
+    // layout: bn2 scale[F] shift[F] | W1[32*F] b1[32] | bn3 scale[32] shift[32] | w2[32] b2 | pooled[kHeadWin][F + 1]
     const int F = L.n_feat;
     const int n_par = 2 * F + 32 * F + 32 + 64 + 32 + 1;
+    float* s_pool = s_par + ((n_par + 3) & ~3);
     for (int i = threadIdx.x; i < n_par; i += blockDim.x) s_par[i] = L.params[i];
-    __syncthreads();
     const float* bn2_s = s_par;
     const float* bn2_b = bn2_s + F;
     const float* w1 = bn2_b + F;
@@ -140,42 +144,48 @@ head_kernel(HeadLaunch L, ChannelTable ct, float* __restrict__ probs, long long 
     const float* bn3_s = b1 + 32;
     const float* bn3_b = bn3_s + 32;
     const float* w2 = bn3_b + 32;
-    const float b2 = w2[32];
 
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    long long local = 0;
-    const int chan = find_channel(ct, chunk_row0 + b, local);
-    if (chan < 0) return;  // gap row: no window starts here
-
-    // AvgPool2d(4): rows 4g..4g+3, real cols 0..3; feature index = c * groups + g   (models.py:229-230)
-    float x[kMaxHeadFeat];
     const int C = L.C, G = L.groups;
-    for (int i = 0; i < F; ++i) x[i] = 0.f;
-    for (int i = 0; i < 4 * G; ++i) {
-        const HeadRow hr = L.rows[i];
-        const __half* base = hr.plane + ((static_cast<long long>(b) + hr.row_shift) * L.wp + 1) * 8;
-        const int g = i >> 2;
+    const int w = threadIdx.x % kHeadWin, g = threadIdx.x / kHeadWin;
+    const int b = blockIdx.x * kHeadWin + w;
+    // AvgPool2d(4): rows 4g..4g+3, real cols 0..3; feature index = c * groups + g   (models.py:229-230)
+    if (b < nb && g < G) {
         for (int kc = 0; kc < C / 8; ++kc) {
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int part = 0; part <= L.split; ++part) {   // [hi | lo] planes: the rounding residual sits C/8 chunks further
+                uint4 v[4][4];
 #pragma unroll
-                for (int cpx = 0; cpx < 4; ++cpx) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(base + (kc + part * (C / 8)) * hr.kc_stride + cpx * 8);
-                    const __half2* vh = reinterpret_cast<const __half2*>(&v);
+                for (int r = 0; r < 4; ++r) {
+                    const HeadRow hr = L.rows[4 * g + r];
+                    const __half* base = hr.plane + ((static_cast<long long>(b) + hr.row_shift) * L.wp + 1) * 8 +
+                                         static_cast<long long>(kc + part * (C / 8)) * hr.kc_stride;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 f = __half22float2(vh[e]);
-                        acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
-                    }
+                    for (int cpx = 0; cpx < 4; ++cpx) v[r][cpx] = *reinterpret_cast<const uint4*>(base + cpx * 8);
                 }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int cpx = 0; cpx < 4; ++cpx) {
+                        const __half2* vh = reinterpret_cast<const __half2*>(&v[r][cpx]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __half22float2(vh[e]);
+                            acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+                        }
+                    }
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[(kc * 8 + e) * G + g] += acc[e];
+            for (int e = 0; e < 8; ++e) s_pool[w * (F + 1) + (kc * 8 + e) * G + g] = acc[e];
         }
     }
-    for (int i = 0; i < F; ++i) x[i] = fmaf(x[i] * (1.f / 16.f), bn2_s[i], bn2_b[i]);
-    float z = b2;
+    __syncthreads();
+    if (g != 0 || b >= nb) return;
+    long long local = 0;
+    const int chan = find_channel(ct, chunk_row0 + b, local);
+    if (chan < 0) return;  // gap row: no window starts here
+    float x[kMaxHeadFeat];
+    for (int i = 0; i < F; ++i) x[i] = fmaf(s_pool[w * (F + 1) + i] * (1.f / 16.f), bn2_s[i], bn2_b[i]);
+    float z = w2[32];
     for (int o = 0; o < 32; ++o) {
         float h = b1[o];
         for (int i = 0; i < F; ++i) h = fmaf(w1[o * F + i], x[i], h);
@@ -203,8 +213,16 @@ cudaError_t launch_stem(const StemLaunch& L, const ChannelTable& ct, const float
 cudaError_t launch_head(const HeadLaunch& L, const ChannelTable& ct, float* probs, long long chunk_row0, int nb,
                         cudaStream_t stream) {
     const int F = L.n_feat;
-    const size_t smem = sizeof(float) * (2 * F + 32 * F + 32 + 64 + 32 + 1);
-    head_kernel<<<(nb + 127) / 128, 128, smem, stream>>>(L, ct, probs, chunk_row0, nb);
+    if (L.groups > 3) return cudaErrorInvalidValue;   // the kernel runs three pooling groups per window (13 rows -> 3 x 4)
+    const int n_par = 2 * F + 32 * F + 32 + 64 + 32 + 1;
+    const size_t smem = sizeof(float) * (((n_par + 3) & ~3) + kHeadWin * (F + 1));
+    static PerDeviceOnce attr_set;
+    if (!attr_set.flag()) {
+        cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set.flag() = true;
+    }
+    head_kernel<<<(nb + kHeadWin - 1) / kHeadWin, 3 * kHeadWin, smem, stream>>>(L, ct, probs, chunk_row0, nb);
     return cudaGetLastError();
 }
 

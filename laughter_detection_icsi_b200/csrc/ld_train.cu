@@ -666,6 +666,7 @@ struct BnHost {
     int fwd_sums = 0, bwd_sums = 0;           // float offsets into the statistics buffer
     int stat_out = 0;                         // float offset into the bn_stats output (mean[C], var[C])
     long long count = 0;                      // elements per channel (B * H * W), set per call
+    bool reduce_fused = false;                // sum g / sum g xhat come from the epilogue of the dgrad GEMM that produces dy
 };
 struct ConvHost {
     std::string name;
@@ -717,6 +718,7 @@ public:
     TPlane dy_last{};
     GemmTuning tune{};
     bool wgrad_mma = true;            // LD_WGRAD=cuda selects the CUDA-core weight-gradient kernel instead
+    bool fuse_bwd_stats = true;       // LD_TRAIN_FUSE_BWD=0: separate bn_bwd_reduce passes everywhere (cross-check)
     int max_batch_seen = 0;
     long long launches = 0;
     // per-call state
@@ -817,6 +819,7 @@ TrainNet* train_create(int max_batch, int num_sms, const NetConfig& cfg, std::st
     n->max_batch = max_batch; n->num_sms = num_sms; n->cfg = cfg;
     n->tune = gemm_tuning_from_env();
     if (const char* v = std::getenv("LD_WGRAD")) n->wgrad_mma = std::string(v) != "cuda";
+    if (const char* v = std::getenv("LD_TRAIN_FUSE_BWD")) n->fuse_bwd_stats = std::atoi(v) != 0;
 
     // ---- topology, parameter table (module registration order of the reference's ResNetBigger) and sizes
     struct LevelSpec { int H, W, C, quad; };
@@ -1109,6 +1112,20 @@ inline unsigned blocks_for(long long n, int threads) { return static_cast<unsign
 // grid of an element-wise grid-stride kernel: enough 256-thread blocks to fill the GPU, no more than the work needs
 inline unsigned ew_grid(const TrainNet* n, long long items) {
     return static_cast<unsigned>(std::max<long long>(1, std::min<long long>((items + 255) / 256, static_cast<long long>(n->num_sms) * 16)));
+}
+
+// Points a data-gradient launch at the BatchNorm whose input gradient it produces: its epilogue then accumulates that
+// BatchNorm's backward sums (GemmBwdStats).  mask_mode 1: y = relu(bn(z) + residual), mask from the stored y; 2: y = relu(bn(z)).
+void set_bwd_stats(TrainNet* n, GemmLaunch& L, const ConvHost& c, int mask_mode, const TPlane* y) {
+    L.stats = n->stats + c.bn.bwd_sums;
+    L.stats_kind = 1;
+    L.bwd.z = c.z.base[0]; L.bwd.z_kc = c.z.kc_stride;
+    L.bwd.y = y ? y->base[0] : nullptr; L.bwd.y_kc = y ? y->kc_stride : 0;
+    L.bwd.fwd_sums = n->stats + c.bn.fwd_sums;
+    L.bwd.gamma = n->params_d + c.bn.gamma_off;
+    L.bwd.beta = n->params_d + c.bn.beta_off;
+    L.bwd.inv_n = 1.f / static_cast<float>(c.bn.count);
+    L.bwd.mask_mode = mask_mode;
 }
 
 cudaError_t run_gemm(TrainNet* n, GemmLaunch& L, const TPlane& geom, cudaStream_t stream, std::string& err) {
@@ -1410,12 +1427,16 @@ cudaError_t train_backward(TrainNet* n, const float* dprobs, float* grads, cudaS
     auto bn_backward = [&](const TPlane& dy, const TPlane& y, int relu, ConvHost& c, int write_g, const TPlane& g_out) {
         float* sums = n->stats + c.bn.bwd_sums;
         const long long work = c.bn.count * (c.cout / 8);
-        const unsigned grid_r = static_cast<unsigned>(std::min<long long>((work + 255) / 256, n->num_sms * 8));
-        bn_bwd_reduce_kernel<<<grid_r, 256, 0, stream>>>(dy, y, relu, c.z, bn_ref(*n, c.bn), B, sums);
+        if (!c.bn.reduce_fused) {   // (fused: the dgrad GEMM that produced dy already accumulated the sums in its epilogue)
+            const unsigned grid_r = static_cast<unsigned>(std::min<long long>((work + 255) / 256, n->num_sms * 8));
+            bn_bwd_reduce_kernel<<<grid_r, 256, 0, stream>>>(dy, y, relu, c.z, bn_ref(*n, c.bn), B, sums);
+            ++n->launches;
+        }
         bn_bwd_apply_kernel<<<ew_grid(n, work), 256, 0, stream>>>(dy, y, relu, c.z, bn_ref(*n, c.bn), sums, B, c.dz, write_g, g_out,
                                                                       grads + c.bn.gamma_off, grads + c.bn.beta_off);
-        n->launches += 2;
+        ++n->launches;
     };
+    for (auto& c : n->convs) c.bn.reduce_fused = false;
 
     for (int bi = static_cast<int>(n->blocks.size()) - 1; bi >= 0; --bi) {
         BlockHost& blk = n->blocks[bi];
@@ -1427,6 +1448,9 @@ cudaError_t train_backward(TrainNet* n, const float* dprobs, float* grads, cudaS
         // y = relu(bn2(z2) + shortcut): g = dy * [y > 0] is the gradient of both summands
         bn_backward(dout, out, 1, c2, 1, blk.g);
         if (cudaError_t e = run_wgrad(n, c2, grads + c2.w_off, stream)) { err = "wgrad " + c2.name; return e; }
+        // dh = conv2^T(dz2); its epilogue also reduces bn1's backward sums (h = relu(bn1(z1)): mask recomputed from z1)
+        if (n->fuse_bwd_stats) { set_bwd_stats(n, c2.bwd, c1, 2, nullptr); c1.bn.reduce_fused = true; }
+        else { c2.bwd.stats = nullptr; c2.bwd.stats_kind = 0; }
         if (cudaError_t e = run_gemm(n, c2.bwd, blk.dh, stream, err)) return e;
         bn_backward(blk.dh, h, 2, c1, 0, blk.g);   // h = relu(bn1(z1)): the mask comes from z1, h is not read
         if (cudaError_t e = run_wgrad(n, c1, grads + c1.w_off, stream)) { err = "wgrad " + c1.name; return e; }
@@ -1435,7 +1459,20 @@ cudaError_t train_backward(TrainNet* n, const float* dprobs, float* grads, cudaS
             bn_backward(blk.g, blk.g, 0, cs, 0, blk.g);
             if (cudaError_t e = run_wgrad(n, cs, grads + cs.w_off, stream)) { err = "wgrad " + cs.name; return e; }
         }
-        // gradient of the block input: conv1^T on dz1 plus the shortcut path, one GEMM launch
+        // gradient of the block input: conv1^T on dz1 plus the shortcut path, one GEMM launch.  With a stride-1 conv1 its output
+        // has the geometry of the previous BatchNorm's z plane, so that BatchNorm's backward sums ride in the epilogue too
+        // (previous block: y = relu(bn2(z2) + shortcut), mask from the stored y; first block: the stem, mask from z0).
+        c1.bwd.stats = nullptr; c1.bwd.stats_kind = 0;
+        if (n->fuse_bwd_stats && c1.stride == 1) {
+            if (bi > 0) {
+                ConvHost& pc2 = n->convs[n->blocks[bi - 1].conv2];
+                set_bwd_stats(n, c1.bwd, pc2, 1, &n->levels[blk.in_level]);
+                pc2.bn.reduce_fused = true;
+            } else {
+                set_bwd_stats(n, c1.bwd, n->convs[0], 2, nullptr);
+                n->convs[0].bn.reduce_fused = true;
+            }
+        }
         if (cudaError_t e = run_gemm(n, c1.bwd, n->dlevels[blk.in_level], stream, err)) return e;
     }
     {   // stem

@@ -83,6 +83,20 @@ __host__ __device__ inline int w_stack_row(int order, int ky) { return order == 
 struct GemmJobTaps {   // where a job's tap program sits in GemmParams::taps
     uint16_t tap0, n_taps, n_stages, pad_;
 };
+// mode 1: BatchNorm-BACKWARD statistics fused into the data-gradient launch that produces dy (GemmParams::stats_kind = 1): the
+// epilogue reduces sum g and sum g * xhat (g = dy * [y > 0], xhat = the BatchNorm's normalised input) from its fp32
+// accumulators into `stats`, which saves the separate reduction pass over dy / y / z.  z and y are plain planes with the
+// pixel geometry of the launch's output.
+struct GemmBwdStats {
+    const void* z;          // conv output the BatchNorm normalised (bf16, chunk-planar)
+    const void* y;          // activation plane for the ReLU mask (mask_mode 1)
+    long long z_kc, y_kc;   // elements between channel chunks
+    const float* fwd_sums;  // [2 cout] sum z, sum z^2 of the forward pass
+    const float* gamma;     // [cout]
+    const float* beta;      // [cout]
+    float inv_n;
+    int32_t mask_mode;      // 0: g = dy;  1: g = dy * [y > 0];  2: g = dy * [z * ya + yb > 0] (y = relu(bn(z)), no residual)
+};
 struct GemmParams {         // the kernel's __grid_constant__ parameter
     // The tap programs of all jobs, densely packed.  They stay in parameter (constant) space on purpose: the issuing thread
     // indexes them with warp-uniform values, so the loads, the descriptor arithmetic and the tcgen05.mma operands all live
@@ -111,6 +125,8 @@ struct GemmParams {         // the kernel's __grid_constant__ parameter
     int32_t n_rings;    // 2: two producer/issuer pipelines over half the stages each; 1: a single ring
     int32_t mode;       // 0: inference (fp16, shift + ReLU epilogue); 1: training (bf16, raw output + channel statistics)
     float* stats;       // mode 1: [2 * cout] per-channel sum and sum of squares (atomically accumulated), or null
+    int32_t stats_kind; // 0: sum z, sum z^2 of the output (BatchNorm forward);  1: sum g, sum g * xhat (BatchNorm backward, `bwd`)
+    GemmBwdStats bwd;
     unsigned long long* prof;  // optional: 8 cycle counters per launch (see ld_gemm.cu), null = off
 };
 struct GemmLaunch : GemmParams {   // host side: the parameters plus the job table gemm_build_launch fills;
