@@ -718,7 +718,9 @@ public:
     TPlane dy_last{};
     GemmTuning tune{};
     bool wgrad_mma = true;            // LD_WGRAD=cuda selects the CUDA-core weight-gradient kernel instead
-    bool fuse_bwd_stats = true;       // LD_TRAIN_FUSE_BWD=0: separate bn_bwd_reduce passes everywhere (cross-check)
+    bool fuse_bwd_stats = false;      // LD_TRAIN_FUSE_BWD=1: BatchNorm-backward sums in the epilogue of the dgrad GEMMs instead of separate
+                                      // bn_bwd_reduce passes.  Measured SLOWER (6.14 vs 5.40 ms per step, profiles/r02): the epilogue of
+                                      // the single-output training GEMMs is already their critical path.  Kept for cross-checking.
     int max_batch_seen = 0;
     long long launches = 0;
     // per-call state

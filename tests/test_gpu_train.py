@@ -308,6 +308,33 @@ def test_every_training_kernel_against_torch_on_its_own_inputs(train_engine):
     assert _rel(rd(3, level), ylast.grad) < PL
 
 
+def test_bn_backward_sums_in_the_gemm_epilogue_agree_with_the_reduction_pass(monkeypatch):
+    """LD_TRAIN_FUSE_BWD=1 folds sum g / sum g*xhat of the BatchNorm backward into the epilogue of the data-gradient GEMM that
+    produces dy (GemmBwdStats).  It is off by default (measured slower); both paths must give the same parameter gradients up
+    to the bf16 rounding of the stored dy plane that only the separate pass sees."""
+    from laughter_detection_icsi_b200.engine import Engine
+    sd, x, labels, mask1, mask2 = make_case(31, 24)
+    grads = {}
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("LD_TRAIN_FUSE_BWD", fuse)
+        eng = Engine(0, chunk_rows=256)
+        try:
+            eng.train_create(32)
+            flat = flat_params(eng, sd)
+            probs, _ = eng.train_forward(flat, x.reshape(24, 100, 44).cuda().contiguous(), mask1.cuda(), mask2.cuda(), 0.5)
+            pr = probs.detach().clone().requires_grad_(True)
+            torch.nn.functional.binary_cross_entropy(pr, labels.cuda()).backward()
+            grads[fuse] = eng.train_backward(pr.grad).cpu().double().numpy()
+            table = eng.train_table["params"]
+        finally:
+            eng.close()
+    a, b = grads["0"], grads["1"]
+    assert np.linalg.norm(a - b) / np.linalg.norm(a) < 2e-2
+    for name, off, n in table:
+        if ".bn" in name or name.startswith("bn1"):
+            assert np.linalg.norm(a[off:off + n] - b[off:off + n]) <= 2e-2 * np.linalg.norm(a[off:off + n]) + 1e-7, name
+
+
 def test_fused_clip_adam_matches_torch_optimizer():
     """K8 (ld_clip_adam_step through train.B200Adam on flat parameters) against clip_grad_norm_ + torch.optim.Adam: same
     parameters after three steps from identical gradients (the two models share the kernels' forward/backward)."""
