@@ -32,10 +32,12 @@ def create_inference_dataloader(audio_path):
     return DataLoader(dataset, batch_size=32)
 
 
-def infer_audio_file(audio_path, model):
-    """Fused path: per-frame probabilities (numpy float32, length T) for one audio file."""
+def infer_audio_file(audio_path, model, as_tensor=False):
+    """Fused path: per-frame probabilities (numpy float32, length T) for one audio file; as_tensor=True leaves them on the
+    GPU (a CUDA float32 tensor) so that the segmenter reads them without a host round trip."""
     feats = compute_features_for_file(audio_path, device=next(model.parameters()).device.index or 0)
-    return model.infer_channel(feats).cpu().numpy()
+    probs = model.infer_channel(feats)
+    return probs if as_tensor else probs.cpu().numpy()
 
 
 def create_training_dataloader(cutset_dir, split, shuffle=False):

@@ -67,7 +67,7 @@ def predict_probs(model, audio_path):
 def load_and_pred(audio_path, model, thresholds, min_lengths, output_dir, save_to_audio_files, save_to_textgrid):
     """Predicts, segments and writes outputs; returns the time taken excluding output files."""
     start_time = time.time()
-    probs = predict_probs(model, audio_path)
+    probs = load_data.infer_audio_file(audio_path, model, as_tensor=True)   # stays on the model's GPU for the segmenter
     file_length = audio_utils.get_audio_length(audio_path)
     fps = len(probs) / float(file_length)
     # the reference disabled laugh_segmenter.lowpass here because it can output probs < 0 (segment_laughter.py:107-108)

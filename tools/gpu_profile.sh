@@ -3,7 +3,7 @@
 #   tools/gpu_profile.sh launches   launch list (gpu__time_duration) of a short bench run
 #   tools/gpu_profile.sh full       --set full capture of the four block1 conv GEMM launches of the timed step
 mkdir -p gpurun_out
-SMALL="python bench.py --channels 1 --minutes 10 --steps 1 --warmup 1 --no-cpu-baseline --train-steps 0"
+SMALL="python bench.py --channels 1 --minutes 10 --steps 1 --warmup 1 --no-cpu-baseline --no-parity --train-steps 0"
 KERNELS='regex:gemm_taps|stem_kernel|head_kernel|fbank_kernel|pcm_sum|segment_'
 $SMALL > gpurun_out/plain_small.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_small.log; exit 1; }
 if [ "$1" = "full" ]; then
