@@ -331,7 +331,7 @@ int64_t ld_gemm_program_json(const ld_config* cfg, char* buf, int64_t cap) {
             s += "{\"conv\":\"" + cs.conv + "\",\"cin\":" + std::to_string(L.cin) + ",\"cout\":" + std::to_string(L.cout) +
                  ",\"w_stack\":" + std::to_string(L.w_stack) + ",\"w_blocks\":" + std::to_string(L.w_blocks) + ",\"ext_alloc\":" + std::to_string(L.ext_alloc) +
                  ",\"groups_per_stage\":" + std::to_string(L.groups_per_stage) + ",\"n_stages\":" + std::to_string(L.n_stages) +
-                 ",\"n_rings\":" + std::to_string(L.n_rings) + ",\"n_issuers\":" + std::to_string(L.n_issuers) + ",\"jobs\":[";
+                 ",\"n_rings\":" + std::to_string(L.n_rings) + ",\"n_issuers\":" + std::to_string(L.n_issuers) + ",\"tmem_cols\":" + std::to_string(L.tmem_cols) + ",\"jobs\":[";
             for (int j = 0; j < L.n_jobs; ++j) {
                 const ld::GemmJob& job = L.jobs[j];
                 if (j) s += ",";

@@ -89,9 +89,12 @@ struct TileWalk {
 // MODE 0: inference -- fp16 operands, epilogue = + folded BatchNorm shift, ReLU, fp16 store (PLAIN or COLSPLIT).
 // MODE 1: training  -- bf16 operands, epilogue = raw conv output as bf16 (PLAIN) and, when L.stats is set, per-channel
 //                      sum / sum of squares of the fp32 accumulators over the real pixels (BatchNorm batch statistics).
-template <int CIN, int COUT, int MODE>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// DUAL: the CTA allocates 256 instead of 512 accumulator columns and half of the shared memory, so that two CTAs share an SM
+// (narrow inference layers, whose small MMAs leave the tensor pipe, the copy engine and the epilogue warps idle in turn).
+template <int CIN, int COUT, int MODE, bool DUAL = false>
+__global__ void __launch_bounds__(kGemmThreads, DUAL ? 2 : 1)
 gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
+    constexpr int kTmemCols = DUAL ? 256 : ld::kTmemCols;
     extern __shared__ __align__(128) uint8_t smem[];
     // the warp index through a shuffle: the compiler then knows it is warp-uniform, and everything the issuing thread derives
     // from it and from the kernel parameters stays on the uniform datapath
@@ -543,12 +546,14 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
 }
 
 // Host launcher.
-template <int CIN, int COUT, int MODE>
+template <int CIN, int COUT, int MODE, bool DUAL = false>
 static cudaError_t launch_typed(const GemmLaunch& h, int m_tiles, int M, int num_sms, cudaStream_t stream) {
+    if (DUAL) num_sms *= 2;   // two resident CTAs per SM
     static PerDeviceOnce attr_set;
     const GemmSmem lay = gemm_smem_layout(CIN, COUT, h.n_wtaps, h.n_jobs, h.ext_alloc, h.groups_per_stage, h.n_stages);
     if (!attr_set.flag()) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_taps_kernel<CIN, COUT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(gemm_taps_kernel<CIN, COUT, MODE, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(gemm_smem_cap(DUAL ? 256 : ld::kTmemCols)));
         if (e != cudaSuccess) return e;
         attr_set.flag() = true;
     }
@@ -570,7 +575,7 @@ static cudaError_t launch_typed(const GemmLaunch& h, int m_tiles, int M, int num
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, gemm_taps_kernel<CIN, COUT, MODE>, static_cast<const GemmParams&>(h), m_tiles, M);
+    return cudaLaunchKernelEx(&cfg, gemm_taps_kernel<CIN, COUT, MODE, DUAL>, static_cast<const GemmParams&>(h), m_tiles, M);
 }
 
 cudaError_t launch_gemm_taps(GemmLaunch& h, int m_tiles, int M, int num_sms, cudaStream_t stream) {
@@ -582,8 +587,11 @@ cudaError_t launch_gemm_taps(GemmLaunch& h, int m_tiles, int M, int num_sms, cud
         if (e != cudaSuccess) { cudaFree(dev); return e; }
         h.jobs_dev = dev;
     }
-#define LD_GEMM_CASE(ci, co) \
-    if (h.mode == 0 && h.cin == ci && h.cout == co) return launch_typed<ci, co, 0>(h, m_tiles, M, num_sms, stream)
+#define LD_GEMM_CASE(ci, co)                                                                                          \
+    if (h.mode == 0 && h.cin == ci && h.cout == co) {                                                                 \
+        if (co <= 32 && h.tmem_cols == 256) return launch_typed<ci, co, 0, (co <= 32)>(h, m_tiles, M, num_sms, stream); \
+        return launch_typed<ci, co, 0>(h, m_tiles, M, num_sms, stream);                                               \
+    }
     LD_GEMM_CASE(64, 64); LD_GEMM_CASE(64, 48); LD_GEMM_CASE(64, 32); LD_GEMM_CASE(64, 16);
     LD_GEMM_CASE(48, 64); LD_GEMM_CASE(48, 48); LD_GEMM_CASE(48, 32); LD_GEMM_CASE(48, 16);
     LD_GEMM_CASE(32, 64); LD_GEMM_CASE(32, 48); LD_GEMM_CASE(32, 32); LD_GEMM_CASE(32, 16);
@@ -604,10 +612,10 @@ void gemm_release(GemmLaunch& h) {
 }
 
 // Chooses the smem ring depth for a launch (host side).
-int gemm_pick_stages(int cin, int cout, int n_wtaps, int n_jobs, int ext_alloc, int groups_per_stage, int max_stages) {
+int gemm_pick_stages(int cin, int cout, int n_wtaps, int n_jobs, int ext_alloc, int groups_per_stage, int max_stages, unsigned smem_cap) {
     if (max_stages > kMaxStages || max_stages < 2) max_stages = kMaxStages;
     for (int n = max_stages; n >= 2; --n) {
-        if (gemm_smem_layout(cin, cout, n_wtaps, n_jobs, ext_alloc, groups_per_stage, n).total <= 227u * 1024u) return n;
+        if (gemm_smem_layout(cin, cout, n_wtaps, n_jobs, ext_alloc, groups_per_stage, n).total <= smem_cap) return n;
     }
     return 0;
 }

@@ -22,6 +22,8 @@ GemmTuning gemm_tuning_from_env() {
     t.issuers_wide = env_int("LD_GEMM_ISSUERS_WIDE", 2);
     t.issuers_narrow = env_int("LD_GEMM_ISSUERS_NARROW", 4);
     t.n_rings_max = env_int("LD_GEMM_RINGS", 2);
+    t.dual_narrow = env_int("LD_GEMM_DUAL", 1);
+    t.issuers_dual = env_int("LD_GEMM_ISSUERS_DUAL", 2);
     return t;
 }
 
@@ -45,6 +47,7 @@ bool shares_input(const HostJob& a, const HostJob& b) {
 }  // namespace
 
 static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, int max_outs, bool pack_all, std::string& err);
+static bool gemm_build_launch_impl(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, std::string& err);
 
 // The caller presets L's header (weights, shift, cin, cout, n_wtaps, w_stack, relu, wp, out_mode, wp2, hp, mode, stats, prof).
 bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, std::string& err) {
@@ -59,13 +62,33 @@ bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
     if (L.w_stack && L.n_wtaps < 9 * L.w_blocks) { err = "stacked weights need a 3x3 kernel"; return false; }
     // cout >= 48: two issuers with 256 accumulator columns each (chains of up to 4 outputs); narrower layers are bound by
     // the issue latency of their small MMAs: four issuers with 128 columns each
+    // narrow inference layers: two CTAs per SM with 256 accumulator columns and half of the shared memory each; if the weights
+    // leave no room for a useful ring in 113 KB (split precision, 64 -> 32), fall back to one CTA per SM
+    // (measured, profiles/r02/gemm_dual_cta_experiment.log: -3.4 ms per step on the cout = 16 layers, +2.5 ms on cout = 32 -> 16 only)
+    if (L.mode == 0 && L.cout <= (tune.dual_narrow >= 2 ? 32 : 16) && tune.dual_narrow) {
+        GemmLaunch trial = L;
+        GemmTuning t2 = tune;
+        t2.dual_narrow = 0;
+        trial.tmem_cols = 256;
+        trial.n_issuers = tune.issuers_dual;
+        std::string e2;
+        if ((trial.n_issuers == 2 || trial.n_issuers == 4) && gemm_build_launch_impl(trial, outs, t2, e2) && trial.n_stages >= 4) {
+            L = trial;
+            return true;
+        }
+    }
+    L.tmem_cols = kTmemCols;
     L.n_issuers = L.cout >= 48 ? tune.issuers_wide : tune.issuers_narrow;
+    return gemm_build_launch_impl(L, outs, tune, err);
+}
+
+bool gemm_build_launch_impl(GemmLaunch& L, const std::vector<HostJob>& outs, const GemmTuning& tune, std::string& err) {
     if (L.n_issuers != 2 && L.n_issuers != 4) { err = "2 or 4 MMA issuers"; return false; }
     // the longest chains whose loads and taps fit a job (stride-2 layers merge nothing: their chains stay short)
     // 1x1 convs (one or two taps per output) share nothing, but several outputs per job still amortise the per-tile costs
     bool pack_all = true;
     for (const auto& o : outs) pack_all = pack_all && o.taps.size() <= 2;
-    const int max_outs = (L.w_stack || pack_all) ? std::max(1, std::min({tune.max_outs, kMaxOuts, kTmemCols / L.n_issuers / L.cout})) : 1;
+    const int max_outs = (L.w_stack || pack_all) ? std::max(1, std::min({tune.max_outs, kMaxOuts, L.tmem_cols / L.n_issuers / L.cout})) : 1;
     auto build = [&]() {
         for (int mo = max_outs; mo >= 1; --mo)
             if (build_with(L, outs, tune, mo, pack_all, err)) return true;
@@ -155,10 +178,11 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
     // ---- 3. smem ring: a stage holds consecutive groups of a job up to ~stage_bytes (small-K layers: fewer barrier trips)
     const int box_bytes = L.ext_alloc * 16 * kchunks;
     L.groups_per_stage = std::max(1, std::min(max_groups, tune.stage_bytes / box_bytes));
-    L.n_stages = gemm_pick_stages(L.cin, L.cout, L.n_wtaps, L.n_jobs, L.ext_alloc, L.groups_per_stage, tune.max_stages);
+    const unsigned cap = gemm_smem_cap(L.tmem_cols);
+    L.n_stages = gemm_pick_stages(L.cin, L.cout, L.n_wtaps, L.n_jobs, L.ext_alloc, L.groups_per_stage, tune.max_stages, cap);
     while (L.n_stages < 4 && L.groups_per_stage > 1) {
         --L.groups_per_stage;
-        L.n_stages = gemm_pick_stages(L.cin, L.cout, L.n_wtaps, L.n_jobs, L.ext_alloc, L.groups_per_stage, tune.max_stages);
+        L.n_stages = gemm_pick_stages(L.cin, L.cout, L.n_wtaps, L.n_jobs, L.ext_alloc, L.groups_per_stage, tune.max_stages, cap);
     }
     if (L.n_stages < 2) { err = "smem ring shorter than two stages"; return false; }
     L.n_rings = (tune.n_rings_max >= 2 && L.n_stages >= 6) ? 2 : 1;
@@ -208,7 +232,7 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
             const bool first = i == 0 || taps[i - 1].group / gps != stage_of;
             const bool last = e == taps.size() || taps[e].group / gps != stage_of;
             const uint32_t col = static_cast<uint32_t>(t.out) * L.cout, ncols = static_cast<uint32_t>(n_merged) * L.cout;
-            if (col + ncols > static_cast<uint32_t>(kTmemCols / L.n_issuers)) { err = "accumulator overflow"; return false; }
+            if (col + ncols > static_cast<uint32_t>(L.tmem_cols / L.n_issuers)) { err = "accumulator overflow"; return false; }
             tapw[n].x = a16 | (first ? kTapFirst : 0u) | (last ? kTapLast : 0u) | (t.half_k ? kTapHalfK : 0u);
             tapw[n].y = b16 | (lbo16 << 16);
             tapw[n].z = col;

@@ -58,7 +58,8 @@ cudaError_t launch_head(const HeadLaunch& L, const ChannelTable& ct, float* prob
 // ld_gemm.cu
 cudaError_t launch_gemm_taps(GemmLaunch& h, int m_tiles, int M, int num_sms, cudaStream_t stream);
 void gemm_release(GemmLaunch& h);   // frees the device copy of the job table
-int gemm_pick_stages(int cin, int cout, int n_wtaps, int n_jobs, int ext_alloc, int groups_per_stage, int max_stages);
+int gemm_pick_stages(int cin, int cout, int n_wtaps, int n_jobs, int ext_alloc, int groups_per_stage, int max_stages,
+                     unsigned smem_cap = 227u * 1024u);
 
 // ld_launch.cpp
 struct HostTap {
@@ -77,6 +78,8 @@ struct HostJob {   // one OUTPUT plane; gemm_build_launch packs chains of them i
 };
 struct GemmTuning {
     int group_span, max_stages, stage_bytes, max_outs, n_rings_max, issuers_wide, issuers_narrow;
+    int dual_narrow;   // inference layers with cout <= 16 (1, default) / <= 32 (2) run two CTAs per SM (256 accumulator columns each)
+    int issuers_dual;  // MMA-issuing warps of such a CTA (2: the SM keeps four issuers and 128 columns per accumulator stage)
 };
 GemmTuning gemm_tuning_from_env();
 bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& jobs, const GemmTuning& tune, std::string& err);

@@ -39,6 +39,9 @@ struct PerDeviceOnce {
     }
 };
 
+// dynamic shared memory a CTA of a conv launch may use: 228 KB per SM with 1 KB reserved per CTA; two CTAs per SM share it
+inline unsigned gemm_smem_cap(int tmem_cols) { return tmem_cols == 256 ? 113u * 1024u : 227u * 1024u; }
+
 enum OutMode : int32_t { OUT_PLAIN = 0, OUT_COLSPLIT = 1 };
 
 // ---- device-side launch description (passed to the kernel BY VALUE as a __grid_constant__ parameter: every field the
@@ -123,6 +126,8 @@ struct GemmParams {         // the kernel's __grid_constant__ parameter
                         // bit 2 no global stores, bit 3 no TMEM reads/clears in the epilogue
     int32_t n_issuers;  // MMA-issuing warps = accumulator stages (2: 256 columns each, 4: 128 columns each)
     int32_t n_rings;    // 2: two producer/issuer pipelines over half the stages each; 1: a single ring
+    int32_t tmem_cols;  // accumulator columns this CTA allocates: 512 (one CTA per SM) or 256 (narrow layers: two CTAs per SM, whose
+                        // barrier / issue / epilogue latencies then overlap)
     int32_t mode;       // 0: inference (fp16, shift + ReLU epilogue); 1: training (bf16, raw output + channel statistics)
     float* stats;       // mode 1: [2 * cout] per-channel sum and sum of squares (atomically accumulated), or null
     int32_t stats_kind; // 0: sum z, sum z^2 of the output (BatchNorm forward);  1: sum g, sum g * xhat (BatchNorm backward, `bwd`)

@@ -69,7 +69,7 @@ def _expand_tap_program(conv):
     products = []
     for job in conv["jobs"]:
         stage, n_first, n_last, n_pass, open_stage = -1, 0, 0, 0, False
-        assert len(job["outs"]) * cout <= 512 // conv["n_issuers"]
+        assert len(job["outs"]) * cout <= conv["tmem_cols"] // conv["n_issuers"]
         for x, y, z, w in job["taps"]:
             a16, b16, lbo16 = x & 0x3FFF, y & 0x3FFF, (y >> 16) & 0x3FFF
             first, last, passing, half_k = bool(x & (1 << 28)), bool(x & (1 << 29)), bool(x & (1 << 30)), int(bool(x & (1 << 27)))
@@ -83,7 +83,7 @@ def _expand_tap_program(conv):
                 assert first
                 n_pass += 1
             col, n = z, (w >> 17) * 8
-            assert w & ((1 << 17) - 1) == 0 and col + n <= 512 // conv["n_issuers"]
+            assert w & ((1 << 17) - 1) == 0 and col + n <= conv["tmem_cols"] // conv["n_issuers"]
             assert n % cout == 0 and col % cout == 0 and n % 16 == 0 and 16 <= n <= 256
             g = stage * gps + a16 // box16
             off = a16 % box16
@@ -135,6 +135,8 @@ def test_tap_program_covers_the_plan(filters, precision):
         assert [tuple(o) for j in gc["jobs"] for o in j["outs"]] == [(j["out0"], j["out1"]) for j in pc["jobs"]]
         merged += len(want) - sum(len(j["taps"]) for j in gc["jobs"])
         assert gc["n_stages"] >= 2 and gc["n_rings"] in (1, 2) and gc["n_issuers"] in (2, 4)
+        # narrow layers run two CTAs per SM (256 accumulator columns, half the shared memory) when their ring still has >= 4 stages
+        assert gc["tmem_cols"] == 512 if gc["cout"] > 32 else gc["tmem_cols"] in (256, 512)
     assert merged > 300, "chains of window-specific rows share their input loads and MMAs"
 
 
