@@ -211,10 +211,27 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
         uint32_t phase = 0;
         long long c_wait = 0;
         TileWalk tw(blockIdx.x + warp * gridDim.x, n_rings * gridDim.x, n_jobs);
+        // L2 prefetch: the ring holds about half a tile of operands, less than the DRAM latency under load covers; the operands
+        // of this producer's tile `l2pf` steps ahead are requested into L2 now, so that their ring loads find them there
+        const int l2pf = L.l2_prefetch;
+        TileWalk tw_pf = tw;
+        for (int i = 0; i < l2pf; ++i) tw_pf.next();
         for (int it = warp; it < my_tiles && warp < n_rings; it += n_rings, tw.next()) {
             const GemmJob& job = s_jobs[tw.job];
             const int p0 = tw.mt * kTileM;
             const int n_groups = job.n_groups;
+            if (l2pf > 0) {
+                if (it + l2pf * n_rings < my_tiles) {
+                    const GemmJob& pj = s_jobs[tw_pf.job];
+                    const int pp0 = tw_pf.mt * kTileM;
+                    for (int c = lane; c < pj.n_groups * kChunks; c += 32) {
+                        const int g = c / kChunks, kc = c - g * kChunks;
+                        const GemmGroup& grp = pj.groups[g];
+                        bulk_prefetch_l2(grp.src + static_cast<long long>(pp0 + grp.shift) * 8 + kc * grp.kc_stride, lbo_a);
+                    }
+                }
+                tw_pf.next();
+            }
             for (int g0 = 0; g0 < n_groups; g0 += gps) {
                 const int ng = min(gps, n_groups - g0);
                 const int n_copies = (L.dbg & 1) ? 1 : ng * kChunks;   // (dbg bit 0: timing experiment, one copy per stage)

@@ -57,6 +57,10 @@ bool gemm_build_launch(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
         const char* p = std::getenv("LD_GEMM_PROF");
         L.dbg = (v && p && std::atoi(p)) ? std::atoi(v) : 0;
     }
+    {
+        const char* v = std::getenv("LD_GEMM_L2PF");
+        L.l2_prefetch = v ? std::atoi(v) : 0;
+    }
     if (L.w_stack && L.w_blocks < 1) L.w_blocks = 1;
     if (!L.w_stack) L.w_blocks = 0;
     if (L.w_stack && L.n_wtaps < 9 * L.w_blocks) { err = "stacked weights need a 3x3 kernel"; return false; }

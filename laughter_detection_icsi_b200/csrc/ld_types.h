@@ -126,6 +126,7 @@ struct GemmParams {         // the kernel's __grid_constant__ parameter
                         // bit 2 no global stores, bit 3 no TMEM reads/clears in the epilogue
     int32_t n_issuers;  // MMA-issuing warps = accumulator stages (2: 256 columns each, 4: 128 columns each)
     int32_t n_rings;    // 2: two producer/issuer pipelines over half the stages each; 1: a single ring
+    int32_t l2_prefetch; // producer: tiles ahead of the shared-memory ring whose operands are requested into L2 (0 = off)
     int32_t tmem_cols;  // accumulator columns this CTA allocates: 512 (one CTA per SM) or 256 (narrow layers: two CTAs per SM, whose
                         // barrier / issue / epilogue latencies then overlap)
     int32_t mode;       // 0: inference (fp16, shift + ReLU epilogue); 1: training (bf16, raw output + channel statistics)

@@ -119,3 +119,48 @@ def test_two_rank_segment_gather_as_flat_buffers(tmp_path):
     assert c.tolist() == [[0], [1]] and d.tolist() == [[0.5, 0.75]]
     back = ldd.unpack_segments(c, d, settings)
     assert back[0][settings[0]].shape == (0, 2) and back[1][settings[0]].tolist() == [[0.5, 0.75]]
+
+
+def _stream_worker(rank, world, port, out_path):
+    import numpy as np
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    settings = [(0.5, 0.0), (0.5, 0.2), (0.9, 0.0)]
+    durations = [3.0] * 11
+    shards = ldd.shard_units(durations, world)
+    group = 2
+    groups_per_rank = [-(-len(s) // group) for s in shards]
+
+    def result(u):
+        return {settings[0]: np.array([[u + 0.125 * i, u + 0.125 * i + 0.1] for i in range(u + 1)], dtype=np.float64).reshape(-1, 2),
+                settings[1]: np.array([[float(u), u + 0.5]]), settings[2]: np.zeros((0, 2))}
+    sg = ldd.StreamingGather(groups_per_rank, settings, len(durations), dst=0)
+    mine = shards[rank]
+    for g0 in range(0, len(mine), group):
+        ids = mine[g0:g0 + group]
+        sg.submit(ids, [result(u) for u in ids])
+    merged = sg.finish()
+    if rank == 0:
+        ok = all(np.array_equal(merged[u][k], result(u)[k]) for u in range(len(durations)) for k in settings)
+        torch.save({"ok": ok, "n": len(merged)}, out_path)
+    else:
+        assert merged is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_streaming_gather_overlaps_transfers_with_work(tmp_path):
+    """bench.py --config corpus: finished groups travel to rank 0 on background threads while the next group is computed."""
+    out = str(tmp_path / "stream.pt")
+    mp.spawn(_stream_worker, args=(3, 29131 + os.getpid() % 500, out), nprocs=3, join=True)
+    r = torch.load(out)
+    assert r["ok"] and r["n"] == 11
+    import numpy as np
+    settings = [(0.5, 0.2)]
+    sg = ldd.StreamingGather([1], settings, 2)          # single process: identity
+    sg.submit([1, 0], [{settings[0]: np.array([[1.0, 2.0]])}, {settings[0]: np.zeros((0, 2))}])
+    got = sg.finish()
+    assert got[1][settings[0]].tolist() == [[1.0, 2.0]] and got[0][settings[0]].shape == (0, 2)
+    buf = ldd.pack_group([4, 9], [{settings[0]: np.array([[0.5, 0.75]])}, {settings[0]: np.zeros((0, 2))}], settings)
+    back = ldd.unpack_group(buf, settings)
+    assert back[4][settings[0]].tolist() == [[0.5, 0.75]] and back[9][settings[0]].shape == (0, 2)
