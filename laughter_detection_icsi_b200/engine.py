@@ -172,6 +172,13 @@ class Engine:
     # ------------------------------------------------------------------------------------------ K4 / K5
     def segment_runs(self, probs, thr_cmp, thr_raw=None, chan_frames=None, cap=None):
         """Maximal runs of clamp(p) > thr per threshold: list (per threshold) of (starts, ends, chans) int32 numpy."""
+        return self.segment_runs_collect(self.segment_runs_launch(probs, thr_cmp, thr_raw, chan_frames, cap))
+
+    # K4 in two phases, so that a caller can queue more GPU work between the launch and the host-side collection (the run lists
+    # of channel c are copied back and filtered on the host while the GPU already works on channel c + 1, pipeline.py)
+    def segment_runs_launch(self, probs, thr_cmp, thr_raw=None, chan_frames=None, cap=None, slot=0):
+        """Launches K4 into the buffers of `slot` on the current stream and starts the copy of the per-threshold counts to
+        pinned host memory; returns a handle for segment_runs_collect.  A slot may be reused once its handle is collected."""
         if not probs.is_cuda or probs.dtype not in (torch.float32, torch.float64):
             raise ValueError("probs must be a float32/float64 CUDA tensor")
         probs = probs.contiguous().reshape(-1)
@@ -181,38 +188,54 @@ class Engine:
         thr_raw = thr_cmp if thr_raw is None else thr_raw
         n_thr = len(thr_cmp)
         cap = int(cap) if cap else max(1024, probs.numel() // 64)
-        while True:
-            key = (n_thr, cap)
-            if getattr(self, "_seg_key", None) != key:   # device lists are reused across calls
-                self._seg_bufs = tuple(torch.empty((n_thr, cap), dtype=torch.int32, device=self.device) for _ in range(3))
-                self._seg_counts = torch.zeros(n_thr, dtype=torch.int32, device=self.device)
-                self._seg_counts_host = torch.zeros(n_thr, dtype=torch.int32, pin_memory=True)
-                self._seg_key = key
-            starts, ends, chans = self._seg_bufs
-            with torch.cuda.device(self.device):
-                check(self.lib.ld_segment_runs(self._h, probs.data_ptr(), int(probs.dtype == torch.float64),
-                                               i64_array(chan_frames), len(chan_frames), f64_array(thr_cmp), f64_array(thr_raw),
-                                               n_thr, starts.data_ptr(), ends.data_ptr(), chans.data_ptr(),
-                                               self._seg_counts.data_ptr(), cap, self._stream()))
-            self._seg_counts_host.copy_(self._seg_counts, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            cnt = self._seg_counts_host.numpy().copy()
-            if cnt.max(initial=0) <= cap:
-                break
-            cap = int(cnt.max()) + 16
-        # D2H of the USED part of every list only, through one pinned staging buffer (3 x sum(count) int32)
+        slots = self.__dict__.setdefault("_seg_slots", {})
+        st = slots.get(slot)
+        if st is None or st["key"] != (n_thr, cap):   # device lists are reused across calls
+            st = {"key": (n_thr, cap),
+                  "bufs": tuple(torch.empty((n_thr, cap), dtype=torch.int32, device=self.device) for _ in range(3)),
+                  "counts": torch.zeros(n_thr, dtype=torch.int32, device=self.device),
+                  "counts_host": torch.zeros(n_thr, dtype=torch.int32, pin_memory=True),
+                  "event": torch.cuda.Event(), "host": None}
+            slots[slot] = st
+        starts, ends, chans = st["bufs"]
+        with torch.cuda.device(self.device):
+            check(self.lib.ld_segment_runs(self._h, probs.data_ptr(), int(probs.dtype == torch.float64),
+                                           i64_array(chan_frames), len(chan_frames), f64_array(thr_cmp), f64_array(thr_raw),
+                                           n_thr, starts.data_ptr(), ends.data_ptr(), chans.data_ptr(),
+                                           st["counts"].data_ptr(), cap, self._stream()))
+        st["counts_host"].copy_(st["counts"], non_blocking=True)
+        st["event"].record(torch.cuda.current_stream(self.device))
+        return {"slot": slot, "probs": probs, "thr_cmp": list(thr_cmp), "thr_raw": list(thr_raw), "chan_frames": chan_frames,
+                "cap": cap, "n_thr": n_thr}
+
+    def segment_runs_collect(self, handle):
+        """Waits for the K4 launch of `handle` only (not for work queued after it) and copies the USED part of every run list
+        back through one pinned staging buffer, on a side stream (3 x sum(count) int32)."""
+        st = self._seg_slots[handle["slot"]]
+        n_thr, cap = handle["n_thr"], handle["cap"]
+        st["event"].synchronize()
+        cnt = st["counts_host"].numpy().copy()
+        if cnt.max(initial=0) > cap:   # rare: a list overflowed its capacity -- run again with room, synchronously
+            return self.segment_runs_collect(self.segment_runs_launch(handle["probs"], handle["thr_cmp"], handle["thr_raw"],
+                                                                      handle["chan_frames"], cap=int(cnt.max()) + 16, slot="retry"))
+        starts, ends, chans = st["bufs"]
         total = int(cnt.sum())
-        if getattr(self, "_seg_host", None) is None or self._seg_host.numel() < 3 * total:
-            self._seg_host = torch.empty(max(3 * total, 3 * 1024), dtype=torch.int32, pin_memory=True)
-        host = self._seg_host
-        off = 0
-        for k in range(n_thr):
-            n = int(cnt[k])
-            for j, buf in enumerate((starts, ends, chans)):
-                if n:
-                    host[off + j * n: off + (j + 1) * n].copy_(buf[k, :n], non_blocking=True)
-            off += 3 * n
-        torch.cuda.current_stream(self.device).synchronize()
+        if st["host"] is None or st["host"].numel() < 3 * total:
+            st["host"] = torch.empty(max(3 * total, 3 * 1024), dtype=torch.int32, pin_memory=True)
+        host = st["host"]
+        if getattr(self, "_seg_copy_stream", None) is None:
+            self._seg_copy_stream = torch.cuda.Stream(device=self.device)
+        side = self._seg_copy_stream
+        side.wait_event(st["event"])
+        with torch.cuda.stream(side):
+            off = 0
+            for k in range(n_thr):
+                n = int(cnt[k])
+                for j, buf in enumerate((starts, ends, chans)):
+                    if n:
+                        host[off + j * n: off + (j + 1) * n].copy_(buf[k, :n], non_blocking=True)
+                off += 3 * n
+        side.synchronize()
         arr = host.numpy()
         out, off = [], 0
         for k in range(n_thr):

@@ -89,11 +89,15 @@ class LaughterPipeline:
 
     def __call__(self, pcm_host, chan_len, durations_s=None):
         """pcm_host: int16 host tensor (pinned for full copy bandwidth). Returns (per-channel instance dicts, frames).
-        The channels are copied on a side stream one by one and the network starts on channel c as soon as it has
-        landed, so all but the first channel's H2D copy overlaps with compute."""
+        Software pipeline over the channels: they are copied on a side stream one by one, the network starts on channel c as
+        soon as it has landed (all but the first H2D copy overlap with compute), and the run lists of channel c are copied
+        back and min-length filtered on the host while the GPU already works on channel c + 1 (K4 in two phases,
+        Engine.segment_runs_launch / _collect) -- only the last channel's D2H + filter is exposed."""
         dev = self.engine.device
         chan_len = [int(n) for n in chan_len]
         pcm_host = pcm_host.reshape(-1)
+        if durations_s is None:
+            durations_s = [n / float(_engine.SAMPLE_RATE) for n in chan_len]
         main = torch.cuda.current_stream(dev)
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=dev)
@@ -107,18 +111,33 @@ class LaughterPipeline:
                 ev.record(self._copy_stream)
                 events.append(ev)
                 off += n
-        probs, frames, off = [], [], 0
-        for n, ev in zip(chan_len, events):
+        out, frames, off, d2h = [], [], 0, 0
+        caps = self.__dict__.setdefault("_chan_caps", {})
+        pending = None   # (handle, frames of that channel, duration)
+
+        def finish(p):
+            nonlocal d2h
+            handle, f, dur, c = p
+            runs = self.engine.segment_runs_collect(handle)
+            caps[c] = max(caps.get(c, 0), max(len(s) for s, _, _ in runs) + 1024)
+            d2h += int(self.engine.last_d2h_bytes)
+            out.append(self.instances(runs, f, [dur])[0])
+
+        for c, (n, ev) in enumerate(zip(chan_len, events)):
             main.wait_event(ev)
             p, f = self.probabilities(pcm_dev[off:off + n], [n])
-            probs.append(p)
+            thr_cmp = laugh_segmenter.comparison_thresholds(self.thresholds, p.dtype == torch.float32)
+            handle = self.engine.segment_runs_launch(p, thr_cmp, self.thresholds, f, cap=caps.get(c), slot=c & 1)
+            if pending is not None:
+                finish(pending)       # host work for channel c - 1 while the GPU runs channel c
+            pending = (handle, f, durations_s[c], c)
             frames += f
             off += n
+        if pending is not None:
+            finish(pending)
         pcm_dev.record_stream(self._copy_stream)
-        runs = self.runs(torch.cat(probs) if len(probs) > 1 else probs[0], frames)
-        if durations_s is None:
-            durations_s = [n / float(_engine.SAMPLE_RATE) for n in chan_len]
-        return self.instances(runs, frames, durations_s), frames
+        self._last_d2h = d2h
+        return out, frames
 
     @staticmethod
     def h2d_bytes(chan_len):
@@ -126,4 +145,4 @@ class LaughterPipeline:
 
     def d2h_bytes(self):
         """Bytes the last `runs` call copied back (counts + the used part of the start/end/channel lists)."""
-        return int(self.engine.last_d2h_bytes)
+        return int(getattr(self, "_last_d2h", self.engine.last_d2h_bytes))
