@@ -204,13 +204,32 @@ def _bn_bwd(g, xh, inv, gamma):
     return dz, sgx.reshape(-1), sg.reshape(-1)
 
 
-def test_every_training_kernel_against_torch_on_its_own_inputs(train_engine):
-    """bf16 rounding noise is amplified chaotically by 20 batch-normalised layers (the CPU oracle with bf16-rounded
+@pytest.mark.parametrize("fuse_bwd_stats", [0, 1])
+def test_every_training_kernel_against_torch_on_its_own_inputs(train_engine, fuse_bwd_stats, monkeypatch):
+    """fuse_bwd_stats = 1: LD_TRAIN_FUSE_BWD=1 folds sum g / sum g*xhat of the BatchNorm backward into the epilogue of the
+    data-gradient GEMM that produces dy (GemmBwdStats; off by default -- measured slower).  Those sums then come from the
+    fp32 accumulators instead of the bf16-stored dy plane this test reads back, hence the wider bound on BatchNorm gradients.
+
+    bf16 rounding noise is amplified chaotically by 20 batch-normalised layers (the CPU oracle with bf16-rounded
     storage deviates from fp64 just as much), so kernel correctness is pinned LOCALLY: every conv output, activation,
     gradient plane and parameter gradient is recomputed with torch float64 from the tensors the kernels themselves
     consumed.  Tolerances: 1e-2 relative L2 for bf16-stored planes, 2e-3 for fp32-accumulated parameter gradients."""
     import torch.nn.functional as F
+    from laughter_detection_icsi_b200.engine import Engine
     eng = train_engine
+    if fuse_bwd_stats:
+        monkeypatch.setenv("LD_TRAIN_FUSE_BWD", "1")
+        eng = Engine(0, chunk_rows=256)
+        eng.train_create(16)
+    try:
+        _layer_local_checks(eng, F, 6e-3 if fuse_bwd_stats else 2e-3)
+    finally:
+        if fuse_bwd_stats:
+            eng.close()
+
+
+def _layer_local_checks(eng, F, PB):
+    """PB: bound on BatchNorm affine gradients (sums over the batch with heavy cancellation)."""
     B, p = 8, 0.5
     sd, x, labels, mask1, mask2 = make_case(21, B)
     flat = flat_params(eng, sd)
@@ -259,12 +278,12 @@ def test_every_training_kernel_against_torch_on_its_own_inputs(train_engine):
             assert _rel(g, g_ref) < PL, pre + " g"
             dz2_ref, dg2, db2 = _bn_bwd(g, xh2, inv2, W[pre + ".bn2.weight"])
             assert _rel(dz2, dz2_ref) < PL, pre + " dz2"
-            assert _rel(gof[pre + ".bn2.weight"], dg2) < PG and _rel(gof[pre + ".bn2.bias"], db2) < PG, pre + " bn2 grads"
+            assert _rel(gof[pre + ".bn2.weight"], dg2) < PB and _rel(gof[pre + ".bn2.bias"], db2) < PB, pre + " bn2 grads"
             assert _rel(dh, F.conv_transpose2d(dz2, w2, padding=1)) < PL, pre + " dh"
             assert _rel(gof[pre + ".conv2.weight"].reshape(w2.shape), torch.nn.grad.conv2d_weight(h, w2.shape, dz2, padding=1)) < PG, pre + " dW2"
             dz1_ref, dg1, db1 = _bn_bwd(dh * (h > 0), xh1, inv1, W[pre + ".bn1.weight"])
             assert _rel(dz1, dz1_ref) < PL, pre + " dz1"
-            assert _rel(gof[pre + ".bn1.weight"], dg1) < PG and _rel(gof[pre + ".bn1.bias"], db1) < PG, pre + " bn1 grads"
+            assert _rel(gof[pre + ".bn1.weight"], dg1) < PB and _rel(gof[pre + ".bn1.bias"], db1) < PB, pre + " bn1 grads"
             assert _rel(gof[pre + ".conv1.weight"].reshape(w1.shape),
                         torch.nn.grad.conv2d_weight(xin, w1.shape, dz1, stride=stride, padding=1)) < PG, pre + " dW1"
             opad = (xin.shape[2] - ((z1.shape[2] - 1) * stride + 1), xin.shape[3] - ((z1.shape[3] - 1) * stride + 1))
@@ -287,7 +306,7 @@ def test_every_training_kernel_against_torch_on_its_own_inputs(train_engine):
     dy0, dz0 = rd(3, 0), rd(2, 0)
     dz0_ref, dg0, db0 = _bn_bwd(dy0 * (y0 > 0), xh0, inv0, W["bn1.weight"])
     assert _rel(dz0, dz0_ref) < PL
-    assert _rel(gof["bn1.weight"], dg0) < PG and _rel(gof["bn1.bias"], db0) < PG
+    assert _rel(gof["bn1.weight"], dg0) < PB and _rel(gof["bn1.bias"], db0) < PB
     assert _rel(gof["conv1.weight"].reshape(64, 1, 3, 3), torch.nn.grad.conv2d_weight(x.double(), (64, 1, 3, 3), dz0, padding=1)) < PG
     # head (fp32 kernels): forward and backward from the last activation the kernels produced
     ylast = rd(1, level).requires_grad_(True)
@@ -306,33 +325,6 @@ def test_every_training_kernel_against_torch_on_its_own_inputs(train_engine):
     print("head gradient errors:", {k: f"{e:.2e}" for k, e in head_err.items()}, "dy_last", f"{_rel(rd(3, level), ylast.grad):.2e}")
     assert max(head_err.values()) < PG, head_err
     assert _rel(rd(3, level), ylast.grad) < PL
-
-
-def test_bn_backward_sums_in_the_gemm_epilogue_agree_with_the_reduction_pass(monkeypatch):
-    """LD_TRAIN_FUSE_BWD=1 folds sum g / sum g*xhat of the BatchNorm backward into the epilogue of the data-gradient GEMM that
-    produces dy (GemmBwdStats).  It is off by default (measured slower); both paths must give the same parameter gradients up
-    to the bf16 rounding of the stored dy plane that only the separate pass sees."""
-    from laughter_detection_icsi_b200.engine import Engine
-    sd, x, labels, mask1, mask2 = make_case(31, 24)
-    grads = {}
-    for fuse in ("0", "1"):
-        monkeypatch.setenv("LD_TRAIN_FUSE_BWD", fuse)
-        eng = Engine(0, chunk_rows=256)
-        try:
-            eng.train_create(32)
-            flat = flat_params(eng, sd)
-            probs, _ = eng.train_forward(flat, x.reshape(24, 100, 44).cuda().contiguous(), mask1.cuda(), mask2.cuda(), 0.5)
-            pr = probs.detach().clone().requires_grad_(True)
-            torch.nn.functional.binary_cross_entropy(pr, labels.cuda()).backward()
-            grads[fuse] = eng.train_backward(pr.grad).cpu().double().numpy()
-            table = eng.train_table["params"]
-        finally:
-            eng.close()
-    a, b = grads["0"], grads["1"]
-    assert np.linalg.norm(a - b) / np.linalg.norm(a) < 2e-2
-    for name, off, n in table:
-        if ".bn" in name or name.startswith("bn1"):
-            assert np.linalg.norm(a[off:off + n] - b[off:off + n]) <= 2e-2 * np.linalg.norm(a[off:off + n]) + 1e-7, name
 
 
 def test_fused_clip_adam_matches_torch_optimizer():
