@@ -80,6 +80,31 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin,
         dst[o] = __float2bfloat16_rn(w[i]);
     }
 }
+// All weight slabs of a step in ONE launch: blockIdx.y selects the item, blockIdx.x strides over its elements.
+struct PackItem {
+    long long w_off;        // offset of the fp32 weights in the parameter vector, or -1: identity slab of `cin` channels
+    __nv_bfloat16* dst;
+    int cout, cin, taps, transpose;
+};
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackItem* __restrict__ items, const float* __restrict__ params) {
+    const PackItem it = items[blockIdx.y];
+    if (it.w_off < 0) {
+        const int C = it.cin;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * C; i += gridDim.x * blockDim.x) {
+            const int k = i / C, n = i % C;
+            it.dst[(static_cast<long long>(k / 8) * C + n) * 8 + (k % 8)] = __float2bfloat16_rn(k == n ? 1.f : 0.f);
+        }
+        return;
+    }
+    const float* w = params + it.w_off;
+    const int cout = it.cout, cin = it.cin, taps = it.taps, n = cout * cin * taps;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int t = i % taps, ci = (i / taps) % cin, co = i / (taps * cin);
+        const long long o = it.transpose ? ((static_cast<long long>(t) * (cout / 8) + co / 8) * cin + ci) * 8 + (co % 8)
+                                         : ((static_cast<long long>(t) * (cin / 8) + ci / 8) * cout + co) * 8 + (ci % 8);
+        it.dst[o] = __float2bfloat16_rn(w[i]);
+    }
+}
 __global__ void pack_identity_kernel(int C, __nv_bfloat16* __restrict__ dst) {   // identity slab [C/8][C][8]
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * C; i += gridDim.x * blockDim.x) {
         const int k = i / C, n = i % C;   // K index, N index
@@ -712,6 +737,8 @@ public:
     BnFinalizeItem* bn_items = nullptr;
     std::vector<BnFinalizeItem> bn_items_host;
     int bn_items_batch = -1;          // batch size the device copy of the table was built for
+    void* pack_items = nullptr;       // device table of the weight slabs pack_all_kernel writes every step
+    int n_pack_items = 0;
     float *x_keep = nullptr, *mask1_keep = nullptr, *mask2_keep = nullptr, *params_keep = nullptr;   // inputs of the last forward
     HeadScratch hs{};
     float *dl1 = nullptr, *dd1 = nullptr, *dpool = nullptr;
@@ -734,6 +761,7 @@ public:
         if (head_scratch) cudaFree(head_scratch);
         if (x_keep) cudaFree(x_keep);
         if (bn_items) cudaFree(bn_items);
+        if (pack_items) cudaFree(pack_items);
         for (auto& c : convs) { gemm_release(c.fwd); gemm_release(c.bwd); }
     }
 
@@ -1196,27 +1224,35 @@ cudaError_t train_forward(TrainNet* n, const float* params, const float* x, int 
     n->keep_scale = 1.f / (1.f - dropout_p);
     n->max_batch_seen = std::max(n->max_batch_seen, B);
     LD_TRY(cudaMemsetAsync(n->stats, 0, n->stats_floats * sizeof(float), stream));
-    // packed bf16 weights from the fp32 master parameters (they change every optimizer step)
-    for (size_t i = 1; i < n->convs.size(); ++i) {
-        ConvHost& c = n->convs[i];
-        const int taps = c.ksize * c.ksize, cnt = c.cout * c.cin * taps;
-        pack_conv_kernel<<<blocks_for(cnt, 256), 256, 0, stream>>>(params + c.w_off, c.cout, c.cin, taps, 0, c.w_fwd);
-        ++n->launches;
-    }
-    for (auto& blk : n->blocks) {
-        ConvHost& c1 = n->convs[blk.conv1];
-        ConvHost& c2 = n->convs[blk.conv2];
-        pack_conv_kernel<<<blocks_for(c2.cout * c2.cin * 9, 256), 256, 0, stream>>>(params + c2.w_off, c2.cout, c2.cin, 9, 1, c2.w_bwd);
-        pack_conv_kernel<<<blocks_for(c1.cout * c1.cin * 9, 256), 256, 0, stream>>>(params + c1.w_off, c1.cout, c1.cin, 9, 1, c1.w_bwd);
-        __nv_bfloat16* slab9 = c1.w_bwd + static_cast<size_t>(9) * c1.cin * c1.cout;
-        if (blk.sc >= 0) {
-            ConvHost& cs = n->convs[blk.sc];
-            pack_conv_kernel<<<blocks_for(cs.cout * cs.cin, 256), 256, 0, stream>>>(params + cs.w_off, cs.cout, cs.cin, 1, 1, slab9);
-        } else {
-            pack_identity_kernel<<<blocks_for(c1.cin * c1.cin, 256), 256, 0, stream>>>(c1.cin, slab9);
+    // packed bf16 weights from the fp32 master parameters (they change every optimizer step): one launch for all slabs
+    if (n->pack_items == nullptr) {
+        std::vector<PackItem> items;
+        for (size_t i = 1; i < n->convs.size(); ++i) {
+            ConvHost& c = n->convs[i];
+            items.push_back({c.w_off, c.w_fwd, c.cout, c.cin, c.ksize * c.ksize, 0});
         }
-        n->launches += 3;
+        for (auto& blk : n->blocks) {
+            ConvHost& c1 = n->convs[blk.conv1];
+            ConvHost& c2 = n->convs[blk.conv2];
+            items.push_back({c2.w_off, c2.w_bwd, c2.cout, c2.cin, 9, 1});
+            items.push_back({c1.w_off, c1.w_bwd, c1.cout, c1.cin, 9, 1});
+            __nv_bfloat16* slab9 = c1.w_bwd + static_cast<size_t>(9) * c1.cin * c1.cout;
+            if (blk.sc >= 0) {
+                ConvHost& cs = n->convs[blk.sc];
+                items.push_back({cs.w_off, slab9, cs.cout, cs.cin, 1, 1});
+            } else {
+                items.push_back({-1, slab9, c1.cin, c1.cin, 1, 0});
+            }
+        }
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cap);
+        if (cap != cudaStreamCaptureStatusNone) { err = "first training step inside a CUDA graph capture: run one eager step first"; return cudaErrorInvalidValue; }
+        LD_TRY(cudaMalloc(reinterpret_cast<void**>(&n->pack_items), items.size() * sizeof(PackItem)));
+        LD_TRY(cudaMemcpy(n->pack_items, items.data(), items.size() * sizeof(PackItem), cudaMemcpyHostToDevice));
+        n->n_pack_items = static_cast<int>(items.size());
     }
+    pack_all_kernel<<<dim3(36, n->n_pack_items), 256, 0, stream>>>(static_cast<const PackItem*>(n->pack_items), params);
+    ++n->launches;
     LD_TRY(cudaGetLastError());
 
     // stem
