@@ -117,6 +117,14 @@ LD_API int ld_resnet_infer_windows(ld_ctx* ctx, const float* feats_d, const int6
 LD_API int ld_gather_windows(ld_ctx* ctx, const float* tracks_d, const int64_t* track_off_d, const int64_t* track_len_d,
                       const int32_t* triples_d, int32_t n_windows, float pad_value, float* out_d, void* stream);
 
+/* Audio ingest (host only, no ld_ctx): decodes a Shorten stream (format versions 1-3, 16-bit signed PCM) -- the payload of
+ * the ICSI corpus' NIST SPHERE files ("sample_coding pcm,embedded-shorten-v2.00"), which the reference reads through lhotse's
+ * Recording.from_file / load_audio (load_data.py:44-45).  data: the bytes after the SPHERE header, starting with "ajkg".
+ * out (may be NULL to query the size): interleaved int16 samples, at most cap; *n_out receives the total sample count over
+ * all channels, *n_chan_out the channel count.  Errors: ld_shorten_last_error(). */
+LD_API int ld_shorten_decode(const uint8_t* data, int64_t n_bytes, int16_t* out, int64_t cap, int32_t* n_chan_out, int64_t* n_out);
+LD_API const char* ld_shorten_last_error(void);
+
 /* K4. Replaces the run detection of laugh_segmenter.get_laughter_instances (laugh_segmenter.py:87-105)
  * for n_thr thresholds at once: maximal runs of fix_over_underflow(p) > thr inside each channel, as
  * (first_frame, last_frame) pairs relative to the channel start.  prob_is_f64: probs_d holds doubles.

@@ -55,6 +55,8 @@ SIGNATURES = {
     "ld_resnet_load_weights": (c_int, [c_void_p, POINTER(LdTensor), c_int32]),
     "ld_resnet_infer_windows": (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int32, c_void_p, c_void_p]),
     "ld_gather_windows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, ctypes.c_float, c_void_p, c_void_p]),
+    "ld_shorten_decode": (c_int, [c_void_p, c_int64, c_void_p, c_int64, POINTER(c_int32), POINTER(c_int64)]),
+    "ld_shorten_last_error": (c_char_p, []),
     "ld_segment_runs": (c_int, [c_void_p, c_void_p, c_int32, POINTER(c_int64), c_int32, POINTER(c_double), POINTER(c_double),
                                 c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "ld_filter_min_length": (c_int64, [POINTER(c_int32), POINTER(c_int32), c_int64, c_double, c_double,

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libld_b200.so")
-SOURCES = ["ld_api.cu", "ld_gemm.cu", "ld_net.cu", "ld_fbank.cu", "ld_segment.cu", "ld_plan.cpp", "ld_launch.cpp", "ld_train.cu", "ld_wgrad.cu", "ld_gather.cu"]
+SOURCES = ["ld_api.cu", "ld_gemm.cu", "ld_net.cu", "ld_fbank.cu", "ld_segment.cu", "ld_plan.cpp", "ld_launch.cpp", "ld_train.cu", "ld_wgrad.cu", "ld_gather.cu", "ld_shorten.cpp"]
 HEADERS = ["ld_ptx.cuh", "ld_types.h", "ld_net.h", "ld_train.h", os.path.join("..", "..", "include", "ld_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -185,10 +185,69 @@ def test_sphere_pcm_ingest(tmp_path):
     le, be, shn = str(tmp_path / "le.sph"), str(tmp_path / "be.sph"), str(tmp_path / "shn.sph")
     write(le, "pcm", "01", pcm.astype("<i2").tobytes())
     write(be, "pcm", "10", pcm.astype(">i2").tobytes())
-    write(shn, "pcm,embedded-shorten-v2.00", "01", b"\\x00" * 100)
+    write(shn, "pcm,embedded-shorten-v2.00", "01", b"\x00" * 100)
     for p in (le, be):
         got, sr = audio_utils.load_wav_int16(p)
         assert sr == 16000 and got.dtype == np.int16 and np.array_equal(got, pcm)
         assert audio_utils.get_audio_length(p) == len(pcm) / 16000.0
-    with pytest.raises(ValueError, match="sph2pipe"):
+    with pytest.raises(ValueError, match="ajkg"):   # announced as shorten, but the payload is not a shorten stream
         audio_utils.load_wav_int16(shn)
+    other = str(tmp_path / "ulaw.sph")
+    write(other, "ulaw", "01", b"\x00" * 100)
+    with pytest.raises(ValueError, match="sph2pipe"):
+        audio_utils.load_wav_int16(other)
+
+
+def test_shorten_decoder_round_trips_an_independent_encoder(tmp_path):
+    """ICSI's channels are shorten-compressed SPHERE files.  No shorten binary or ICSI file is available offline (parity
+    unpinned), so the C decoder (ld_shorten_decode) is exercised against tests/shorten_encoder.py on every block command:
+    DIFF0-3, QLPC, ZERO, BITSHIFT, BLOCKSIZE (short last block), VERBATIM, running-mean offsets, mono and stereo, versions 1-3."""
+    import ctypes
+    import shorten_encoder as se
+    from laughter_detection_icsi_b200 import _native
+    lib = _native.load_library()
+
+    def decode(stream):
+        data = np.frombuffer(stream, dtype=np.uint8)
+        n, ch = ctypes.c_int64(0), ctypes.c_int32(0)
+        assert lib.ld_shorten_decode(data.ctypes.data, data.size, None, 0, ctypes.byref(ch), ctypes.byref(n)) == 0, lib.ld_shorten_last_error()
+        out = np.empty(n.value, dtype=np.int16)
+        assert lib.ld_shorten_decode(data.ctypes.data, data.size, out.ctypes.data, out.size, ctypes.byref(ch), ctypes.byref(n)) == 0
+        return out, ch.value
+
+    rng = np.random.default_rng(7)
+    speech = synth.synth_channel(16000 + 77, meeting=8).numpy().astype(np.int64)
+    walk = np.clip(np.cumsum(rng.integers(-300, 301, 5000)) + 1500, -32768, 32767)      # DC offset: exercises the running mean
+    cmds = [se.FN_DIFF0, se.FN_DIFF1, se.FN_DIFF2, se.FN_DIFF3, se.FN_QLPC]
+    for version in (1, 2, 3):
+        for nmean in (0, 4):
+            plan = lambda b, c: (cmds[(b + c) % 5], 0, [21, -9] if cmds[(b + c) % 5] == se.FN_QLPC else None)
+            for sig in (speech, walk):
+                got, ch = decode(se.encode([sig], version=version, nmean=nmean, plan=plan, verbatim=b"RIFFhdr"))
+                assert ch == 1 and np.array_equal(got, sig.astype(np.int16)), (version, nmean)
+    # stereo, a silent (ZERO) block, a bit-shifted stretch (samples multiples of 4), block size 64
+    left = walk[:1000].copy(); left[256:320] = 0
+    right = (rng.integers(-2000, 2000, 1000) // 4) * 4
+    plan = lambda b, c: ((se.FN_ZERO if (c == 0 and b == 4) else se.FN_DIFF2), (2 if c == 1 else 0), None)
+    got, ch = decode(se.encode([left, right], version=2, blocksize=64, nmean=4, plan=plan))
+    assert ch == 2 and np.array_equal(got.reshape(-1, 2)[:, 0], left.astype(np.int16)) and np.array_equal(got.reshape(-1, 2)[:, 1], right.astype(np.int16))
+    # malformed streams fail loudly
+    bad = np.frombuffer(b"ajkg\x02" + b"\x00" * 64, dtype=np.uint8)
+    n = ctypes.c_int64(0)
+    assert lib.ld_shorten_decode(bad.ctypes.data, bad.size, None, 0, None, ctypes.byref(n)) != 0
+    # the SPHERE loader: header + embedded shorten stream, count and checksum verified
+    pcm = speech.astype(np.int16)
+    stream = se.encode([speech], version=2, nmean=4)
+    checksum = int(pcm.view(np.uint16).astype(np.uint64).sum() & 0xFFFF)
+    head = ("NIST_1A\n   1024\nsample_count -i %d\nsample_rate -i 16000\nchannel_count -i 1\nsample_n_bytes -i 2\n"
+            "sample_byte_format -s2 01\nsample_coding -s26 pcm,embedded-shorten-v2.00\nsample_checksum -i %d\nend_head\n" % (len(pcm), checksum)).encode()
+    path = str(tmp_path / "chan0.sph")
+    with open(path, "wb") as f:
+        f.write(head + b" " * (1024 - len(head)) + stream)
+    got, sr = audio_utils.load_wav_int16(path)
+    assert sr == 16000 and np.array_equal(got, pcm) and audio_utils.get_audio_length(path) == len(pcm) / 16000.0
+    with open(path, "wb") as f:
+        f.write(head.replace(b"sample_checksum -i %d" % checksum, b"sample_checksum -i %d" % ((checksum + 1) & 0xFFFF)) + b" " * 1024)
+        f.seek(1024); f.write(stream)
+    with pytest.raises(ValueError, match="checksum"):
+        audio_utils.load_wav_int16(path)
