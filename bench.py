@@ -292,7 +292,8 @@ def run_b200(args):
 
     thresholds, min_lengths = synth.eval_grid()
     sd = synth.synthetic_state_dict()
-    pipe = LaughterPipeline(sd, device=local_rank, thresholds=thresholds, min_lengths=min_lengths, precision=args.precision)
+    pipe = LaughterPipeline(sd, device=local_rank, thresholds=thresholds, min_lengths=min_lengths, precision=args.precision,
+                            chunk_rows=args.chunk_rows)
     eng = pipe.engine
     n_samples = int(args.minutes * 60 * 16000)
     pcm_dev, chan_len = synth.synth_meeting(args.channels, n_samples, meeting=rank, device=f"cuda:{local_rank}")
@@ -688,6 +689,7 @@ def main():
     ap.add_argument("--channels", type=int, default=6, help="channels per GPU per step (one meeting)")
     ap.add_argument("--minutes", type=float, default=60.0, help="minutes of audio per channel")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "split"], help="conv-stack arithmetic (DESIGN.md section 7)")
+    ap.add_argument("--chunk-rows", type=int, default=0, help="window starts per pass of the conv stack (0 = the library default, 32768)")
     ap.add_argument("--corpus-meetings", type=int, default=75)
     ap.add_argument("--feature-channels", type=int, default=64, help="--config features: channel-hours per ld_fbank_i16 call")
     ap.add_argument("--cpu-sample-seconds", type=float, default=20.0, help="audio seconds per CPU-reference step")
