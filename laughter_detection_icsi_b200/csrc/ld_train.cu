@@ -70,16 +70,6 @@ __device__ __forceinline__ void bn_mean_inv(const BnRef& bn, int C, int c, float
 // W (cout, cin, taps) fp32 -> bf16 UMMA B-operand slabs [slab][K/8][N][8].
 //   transpose = 0 (forward):  K = cin,  N = cout : slab[t][ci/8][co][ci%8] = W[co][ci][t]
 //   transpose = 1 (dgrad):    K = cout, N = cin  : slab[t][co/8][ci][co%8] = W[co][ci][t]
-__global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int taps, int transpose,
-                                 __nv_bfloat16* __restrict__ dst) {
-    const int n = cout * cin * taps;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int t = i % taps, ci = (i / taps) % cin, co = i / (taps * cin);
-        const long long o = transpose ? ((static_cast<long long>(t) * (cout / 8) + co / 8) * cin + ci) * 8 + (co % 8)
-                                      : ((static_cast<long long>(t) * (cin / 8) + ci / 8) * cout + co) * 8 + (ci % 8);
-        dst[o] = __float2bfloat16_rn(w[i]);
-    }
-}
 // All weight slabs of a step in ONE launch: blockIdx.y selects the item, blockIdx.x strides over its elements.
 struct PackItem {
     long long w_off;        // offset of the fp32 weights in the parameter vector, or -1: identity slab of `cin` channels
@@ -103,12 +93,6 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackItem* __restric
         const long long o = it.transpose ? ((static_cast<long long>(t) * (cout / 8) + co / 8) * cin + ci) * 8 + (co % 8)
                                          : ((static_cast<long long>(t) * (cin / 8) + ci / 8) * cout + co) * 8 + (ci % 8);
         it.dst[o] = __float2bfloat16_rn(w[i]);
-    }
-}
-__global__ void pack_identity_kernel(int C, __nv_bfloat16* __restrict__ dst) {   // identity slab [C/8][C][8]
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * C; i += gridDim.x * blockDim.x) {
-        const int k = i / C, n = i % C;   // K index, N index
-        dst[(static_cast<long long>(k / 8) * C + n) * 8 + (k % 8)] = __float2bfloat16_rn(k == n ? 1.f : 0.f);
     }
 }
 
