@@ -44,6 +44,15 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
         v[2 * e] = f.x; v[2 * e + 1] = f.y;
     }
 }
+__device__ __forceinline__ uint4 load8raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        v[2 * e] = f.x; v[2 * e + 1] = f.y;
+    }
+}
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
     uint4 raw;
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
@@ -220,6 +229,8 @@ __device__ __forceinline__ void bn_coef_setup(BnCoef& s, const BnRef& bn, int C)
 // groups of 32 consecutive real pixels (a 512-byte contiguous run of every plane it touches) with stride n_warps / chunks,
 // so the per-channel coefficients sit in registers and the reductions stay in registers until the end.  All index math is
 // 32-bit (B * H * W <= 1024 * 100 * 44).
+constexpr int kEwUnroll = 4;   // pixel groups whose loads an element-wise BatchNorm kernel keeps in flight per warp
+constexpr int kEwUnrollBwdApply = 2;   // (three loads and two stores per group: 4 would spill at two CTAs per SM)
 struct EwWalk {
     int kc, lane, P, W, H;
     unsigned group, group_stride, n_groups, magic_w, magic_h;
@@ -256,7 +267,7 @@ __device__ __forceinline__ long long any_off(const TPlane& t, int b, int r, int 
 
 // y = act( bn(z) [+ res] ),  res = plane value (res_mode 1) or bn_s(zs) (res_mode 2).  z and res planes are plain; y may be
 // plain or quad.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_apply_kernel(TPlane z, BnRef bn, int relu, int res_mode, TPlane res, BnRef bn_res, TPlane y, int B) {
     __shared__ BnCoef s, sr;
     const int C = z.C;
@@ -271,21 +282,38 @@ bn_apply_kernel(TPlane z, BnRef bn, int relu, int res_mode, TPlane res, BnRef bn
         ya[e] = s.ya[kc * 8 + e]; yb[e] = s.yb[kc * 8 + e];
         ra[e] = res_mode == 2 ? sr.ya[kc * 8 + e] : 1.f; rb[e] = res_mode == 2 ? sr.yb[kc * 8 + e] : 0.f;
     }
-    for (unsigned g = w.group; g < w.n_groups; g += w.group_stride) {
-        int b, r0, c0, which;
-        if (!w.pixel(g, b, r0, c0)) continue;
-        float v[8], o[8], rv[8];
-        const long long pz = plain_off(z, b, r0, c0);   // z and res are plain planes of the same geometry
-        load8(z.base[0] + kc * z.kc_stride + pz, v);
-        if (res_mode != 0) load8(res.base[0] + kc * res.kc_stride + pz, rv);
+    // kEwUnroll groups per iteration: all their 16-byte loads are issued before the first is consumed (memory-level parallelism)
+    for (unsigned g0 = w.group; g0 < w.n_groups; g0 += kEwUnroll * w.group_stride) {
+        bool live[kEwUnroll];
+        int bb[kEwUnroll], rr[kEwUnroll], cc[kEwUnroll];
+        long long pz[kEwUnroll];
+        uint4 qz[kEwUnroll], qr[kEwUnroll];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float a = fmaf(v[e], ya[e], yb[e]);
-            if (res_mode != 0) a += fmaf(rv[e], ra[e], rb[e]);
-            o[e] = relu ? fmaxf(a, 0.f) : a;
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const unsigned g = g0 + u * w.group_stride;
+            live[u] = g < w.n_groups && w.pixel(g, bb[u], rr[u], cc[u]);
+            if (live[u]) {
+                pz[u] = plain_off(z, bb[u], rr[u], cc[u]);   // z and res are plain planes of the same geometry
+                qz[u] = load8raw(z.base[0] + kc * z.kc_stride + pz[u]);
+                if (res_mode != 0) qr[u] = load8raw(res.base[0] + kc * res.kc_stride + pz[u]);
+            }
         }
-        const long long py = any_off(y, b, r0, c0, pz, which);
-        store8(y.base[which] + kc * y.kc_stride + py, o);
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            if (!live[u]) continue;
+            float v[8], o[8], rv[8];
+            unpack8(qz[u], v);
+            if (res_mode != 0) unpack8(qr[u], rv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float a = fmaf(v[e], ya[e], yb[e]);
+                if (res_mode != 0) a += fmaf(rv[e], ra[e], rb[e]);
+                o[e] = relu ? fmaxf(a, 0.f) : a;
+            }
+            int which;
+            const long long py = any_off(y, bb[u], rr[u], cc[u], pz[u], which);
+            store8(y.base[which] + kc * y.kc_stride + py, o);
+        }
     }
 }
 
@@ -293,7 +321,7 @@ bn_apply_kernel(TPlane z, BnRef bn, int relu, int res_mode, TPlane res, BnRef bn
 // g = dy * [y > 0] (relu) ; reductions sum g, sum g*xhat per channel.
 // relu = 2: y = relu(bn(z)) without a residual, so [y > 0] = [z * ya + yb > 0] is recomputed from z with the very expression the
 // forward pass evaluated (bn_apply_kernel) and the y plane is not read at all.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, int B, float* __restrict__ sums /*[2C]*/) {
     __shared__ float s_acc[128];
     __shared__ BnCoef s;
@@ -309,21 +337,36 @@ bn_bwd_reduce_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, int B, f
         xa[e] = s.xa[kc * 8 + e]; xb[e] = s.xb[kc * 8 + e]; ya[e] = s.ya[kc * 8 + e]; yb[e] = s.yb[kc * 8 + e];
         sg[e] = 0.f; sx[e] = 0.f;
     }
-    for (unsigned g = w.group; g < w.n_groups; g += w.group_stride) {
-        int b, r0, c0, which;
-        if (!w.pixel(g, b, r0, c0)) continue;
-        float gg[8], zz[8], yy[8];
-        const long long pz = plain_off(z, b, r0, c0);   // dy and y share one geometry (plain like z, or quad)
-        const long long pd = any_off(dy, b, r0, c0, pz, which);
-        load8(dy.base[which] + kc * dy.kc_stride + pd, gg);
-        if (relu == 1) load8(y.base[which] + kc * y.kc_stride + pd, yy);
-        load8(z.base[0] + kc * z.kc_stride + pz, zz);
+    for (unsigned g0 = w.group; g0 < w.n_groups; g0 += kEwUnroll * w.group_stride) {
+        bool live[kEwUnroll];
+        uint4 qg[kEwUnroll], qy[kEwUnroll], qz[kEwUnroll];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const bool off = relu == 1 ? !(yy[e] > 0.f) : (relu == 2 ? !(fmaf(zz[e], ya[e], yb[e]) > 0.f) : false);
-            const float ge = off ? 0.f : gg[e];
-            sg[e] += ge;
-            sx[e] = fmaf(ge, fmaf(zz[e], xa[e], xb[e]), sx[e]);
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const unsigned g = g0 + u * w.group_stride;
+            int b, r0, c0, which;
+            live[u] = g < w.n_groups && w.pixel(g, b, r0, c0);
+            if (live[u]) {
+                const long long pz = plain_off(z, b, r0, c0);   // dy and y share one geometry (plain like z, or quad)
+                const long long pd = any_off(dy, b, r0, c0, pz, which);
+                qg[u] = load8raw(dy.base[which] + kc * dy.kc_stride + pd);
+                if (relu == 1) qy[u] = load8raw(y.base[which] + kc * y.kc_stride + pd);
+                qz[u] = load8raw(z.base[0] + kc * z.kc_stride + pz);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            if (!live[u]) continue;
+            float gg[8], zz[8], yy[8];
+            unpack8(qg[u], gg);
+            if (relu == 1) unpack8(qy[u], yy);
+            unpack8(qz[u], zz);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const bool off = relu == 1 ? !(yy[e] > 0.f) : (relu == 2 ? !(fmaf(zz[e], ya[e], yb[e]) > 0.f) : false);
+                const float ge = off ? 0.f : gg[e];
+                sg[e] += ge;
+                sx[e] = fmaf(ge, fmaf(zz[e], xa[e], xb[e]), sx[e]);
+            }
         }
     }
 #pragma unroll
@@ -347,7 +390,7 @@ bn_bwd_reduce_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, int B, f
 
 // dz = gamma * inv * (g - mean(g) - xhat * mean(g xhat)) -> dz plane (plain); optionally g -> g_out (plain);
 // block 0 also writes dgamma = sum g xhat, dbeta = sum g.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, const float* __restrict__ sums, int B, TPlane dz, int write_g,
                     TPlane g_out, float* __restrict__ dgamma, float* __restrict__ dbeta) {
     __shared__ BnCoef s;
@@ -367,24 +410,40 @@ bn_bwd_apply_kernel(TPlane dy, TPlane y, int relu, TPlane z, BnRef bn, const flo
         xa[e] = s.xa[c]; xb[e] = s.xb[c]; ya[e] = s.ya[c]; yb[e] = s.yb[c];
         c1[e] = sums[c] * bn.inv_n; c2[e] = sums[C + c] * bn.inv_n;
     }
-    for (unsigned g = w.group; g < w.n_groups; g += w.group_stride) {
-        int b, r0, c0, which;
-        if (!w.pixel(g, b, r0, c0)) continue;
-        float gg[8], zz[8], yy[8], o[8];
-        const long long pz = plain_off(z, b, r0, c0);   // dy and y share one geometry (plain like z, or quad); dz, g_out are plain
-        const long long pd = any_off(dy, b, r0, c0, pz, which);
-        load8(dy.base[which] + kc * dy.kc_stride + pd, gg);
-        if (relu == 1) load8(y.base[which] + kc * y.kc_stride + pd, yy);
-        load8(z.base[0] + kc * z.kc_stride + pz, zz);
+    for (unsigned g0 = w.group; g0 < w.n_groups; g0 += kEwUnrollBwdApply * w.group_stride) {
+        bool live[kEwUnrollBwdApply];
+        long long pzs[kEwUnrollBwdApply];
+        uint4 qg[kEwUnrollBwdApply], qy[kEwUnrollBwdApply], qz[kEwUnrollBwdApply];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            if (relu == 1 && !(yy[e] > 0.f)) gg[e] = 0.f;
-            if (relu == 2 && !(fmaf(zz[e], ya[e], yb[e]) > 0.f)) gg[e] = 0.f;   // [y > 0] recomputed from z (no residual)
-            const float xh = fmaf(zz[e], xa[e], xb[e]);
-            o[e] = ya[e] * (gg[e] - c1[e] - xh * c2[e]);
+        for (int u = 0; u < kEwUnrollBwdApply; ++u) {
+            const unsigned g = g0 + u * w.group_stride;
+            int b, r0, c0, which;
+            live[u] = g < w.n_groups && w.pixel(g, b, r0, c0);
+            if (live[u]) {
+                pzs[u] = plain_off(z, b, r0, c0);   // dy and y share one geometry (plain like z, or quad); dz, g_out are plain
+                const long long pd = any_off(dy, b, r0, c0, pzs[u], which);
+                qg[u] = load8raw(dy.base[which] + kc * dy.kc_stride + pd);
+                if (relu == 1) qy[u] = load8raw(y.base[which] + kc * y.kc_stride + pd);
+                qz[u] = load8raw(z.base[0] + kc * z.kc_stride + pzs[u]);
+            }
         }
-        store8(dz.base[0] + kc * dz.kc_stride + pz, o);
-        if (write_g) store8(g_out.base[0] + kc * g_out.kc_stride + pz, gg);
+#pragma unroll
+        for (int u = 0; u < kEwUnrollBwdApply; ++u) {
+            if (!live[u]) continue;
+            float gg[8], zz[8], yy[8], o[8];
+            unpack8(qg[u], gg);
+            if (relu == 1) unpack8(qy[u], yy);
+            unpack8(qz[u], zz);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (relu == 1 && !(yy[e] > 0.f)) gg[e] = 0.f;
+                if (relu == 2 && !(fmaf(zz[e], ya[e], yb[e]) > 0.f)) gg[e] = 0.f;   // [y > 0] recomputed from z (no residual)
+                const float xh = fmaf(zz[e], xa[e], xb[e]);
+                o[e] = ya[e] * (gg[e] - c1[e] - xh * c2[e]);
+            }
+            store8(dz.base[0] + kc * dz.kc_stride + pzs[u], o);
+            if (write_g) store8(g_out.base[0] + kc * g_out.kc_stride + pzs[u], gg);
+        }
     }
 }
 
