@@ -780,6 +780,12 @@ public:
     BnFinalizeItem* bn_items = nullptr;
     std::vector<BnFinalizeItem> bn_items_host;
     int bn_items_batch = -1;          // batch size the device copy of the table was built for
+    // weight gradients run on a side stream: they only feed the parameter gradients, so they overlap the BatchNorm element-wise
+    // passes of the data-gradient chain (tensor-bound next to HBM-bound work; ~200 KB + ~2 KB of shared memory share an SM)
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> fork_events;
+    cudaEvent_t join_event = nullptr;
+    bool side_wgrad = true;           // LD_TRAIN_SIDE=0: everything on the caller's stream
     void* pack_items = nullptr;       // device table of the weight slabs pack_all_kernel writes every step
     int n_pack_items = 0;
     float *x_keep = nullptr, *mask1_keep = nullptr, *mask2_keep = nullptr, *params_keep = nullptr;   // inputs of the last forward
@@ -805,6 +811,9 @@ public:
         if (x_keep) cudaFree(x_keep);
         if (bn_items) cudaFree(bn_items);
         if (pack_items) cudaFree(pack_items);
+        for (auto e : fork_events) if (e) cudaEventDestroy(e);
+        if (join_event) cudaEventDestroy(join_event);
+        if (side) cudaStreamDestroy(side);
         for (auto& c : convs) { gemm_release(c.fwd); gemm_release(c.bwd); }
     }
 
@@ -893,6 +902,14 @@ TrainNet* train_create(int max_batch, int num_sms, const NetConfig& cfg, std::st
     n->tune = gemm_tuning_from_env();
     if (const char* v = std::getenv("LD_WGRAD")) n->wgrad_mma = std::string(v) != "cuda";
     if (const char* v = std::getenv("LD_TRAIN_FUSE_BWD")) n->fuse_bwd_stats = std::atoi(v) != 0;
+    if (const char* v = std::getenv("LD_TRAIN_SIDE")) n->side_wgrad = std::atoi(v) != 0;
+    if (n->side_wgrad) {
+        bool ok = cudaStreamCreateWithFlags(&n->side, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&n->join_event, cudaEventDisableTiming) == cudaSuccess;
+        n->fork_events.resize(32, nullptr);
+        for (auto& e : n->fork_events) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { err = "could not create the side stream for the weight gradients"; delete n; return nullptr; }
+    }
 
     // ---- topology, parameter table (module registration order of the reference's ResNetBigger) and sizes
     struct LevelSpec { int H, W, C, quad; };
@@ -1505,6 +1522,15 @@ cudaError_t train_backward(TrainNet* n, const float* dprobs, float* grads, cudaS
     ++n->launches;
     LD_TRY(cudaGetLastError());
 
+    // weight gradient of conv c on the side stream, after everything queued on `stream` so far (its dz is complete)
+    size_t n_fork = 0;
+    auto fork_side = [&]() -> cudaStream_t {
+        if (!n->side_wgrad || n_fork >= n->fork_events.size()) return stream;
+        cudaEvent_t ev = n->fork_events[n_fork++];
+        if (cudaEventRecord(ev, stream) != cudaSuccess || cudaStreamWaitEvent(n->side, ev, 0) != cudaSuccess) return stream;
+        return n->side;
+    };
+    auto wgrad = [&](const ConvHost& c) -> cudaError_t { return run_wgrad(n, c, grads + c.w_off, fork_side()); };
     auto bn_backward = [&](const TPlane& dy, const TPlane& y, int relu, ConvHost& c, int write_g, const TPlane& g_out) {
         float* sums = n->stats + c.bn.bwd_sums;
         const long long work = c.bn.count * (c.cout / 8);
@@ -1528,17 +1554,17 @@ cudaError_t train_backward(TrainNet* n, const float* dprobs, float* grads, cudaS
         const TPlane& h = n->levels[blk.h_level];
         // y = relu(bn2(z2) + shortcut): g = dy * [y > 0] is the gradient of both summands
         bn_backward(dout, out, 1, c2, 1, blk.g);
-        if (cudaError_t e = run_wgrad(n, c2, grads + c2.w_off, stream)) { err = "wgrad " + c2.name; return e; }
+        if (cudaError_t e = wgrad(c2)) { err = "wgrad " + c2.name; return e; }
         // dh = conv2^T(dz2); its epilogue also reduces bn1's backward sums (h = relu(bn1(z1)): mask recomputed from z1)
         if (n->fuse_bwd_stats) { set_bwd_stats(n, c2.bwd, c1, 2, nullptr); c1.bn.reduce_fused = true; }
         else { c2.bwd.stats = nullptr; c2.bwd.stats_kind = 0; }
         if (cudaError_t e = run_gemm(n, c2.bwd, blk.dh, stream, err)) return e;
         bn_backward(blk.dh, h, 2, c1, 0, blk.g);   // h = relu(bn1(z1)): the mask comes from z1, h is not read
-        if (cudaError_t e = run_wgrad(n, c1, grads + c1.w_off, stream)) { err = "wgrad " + c1.name; return e; }
+        if (cudaError_t e = wgrad(c1)) { err = "wgrad " + c1.name; return e; }
         if (blk.sc >= 0) {
             ConvHost& cs = n->convs[blk.sc];
             bn_backward(blk.g, blk.g, 0, cs, 0, blk.g);
-            if (cudaError_t e = run_wgrad(n, cs, grads + cs.w_off, stream)) { err = "wgrad " + cs.name; return e; }
+            if (cudaError_t e = wgrad(cs)) { err = "wgrad " + cs.name; return e; }
         }
         // gradient of the block input: conv1^T on dz1 plus the shortcut path, one GEMM launch.  With a stride-1 conv1 its output
         // has the geometry of the previous BatchNorm's z plane, so that BatchNorm's backward sums ride in the epilogue too
@@ -1559,10 +1585,14 @@ cudaError_t train_backward(TrainNet* n, const float* dprobs, float* grads, cudaS
     {   // stem
         ConvHost& c = n->convs[0];
         bn_backward(n->dlevels[0], n->levels[0], 2, c, 0, c.dz);
-        stem_wgrad_kernel<<<n->num_sms * 4, 256, 0, stream>>>(n->x_d, B, n->cfg.H, n->cfg.W, c.dz, grads + c.w_off);
+        stem_wgrad_kernel<<<n->num_sms * 4, 256, 0, fork_side()>>>(n->x_d, B, n->cfg.H, n->cfg.W, c.dz, grads + c.w_off);
         ++n->launches;
     }
     LD_TRY(cudaGetLastError());
+    if (n_fork > 0) {   // join: the caller's stream continues (optimiser) only after every weight gradient has landed
+        LD_TRY(cudaEventRecord(n->join_event, n->side));
+        LD_TRY(cudaStreamWaitEvent(stream, n->join_event, 0));
+    }
     return cudaSuccess;
 }
 
