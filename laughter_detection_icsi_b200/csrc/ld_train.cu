@@ -780,12 +780,14 @@ public:
     BnFinalizeItem* bn_items = nullptr;
     std::vector<BnFinalizeItem> bn_items_host;
     int bn_items_batch = -1;          // batch size the device copy of the table was built for
-    // weight gradients run on a side stream: they only feed the parameter gradients, so they overlap the BatchNorm element-wise
-    // passes of the data-gradient chain (tensor-bound next to HBM-bound work; ~200 KB + ~2 KB of shared memory share an SM)
+    // optional: weight gradients on a side stream -- they only feed the parameter gradients, so they could overlap the BatchNorm
+    // element-wise passes of the data-gradient chain (tensor-bound next to HBM-bound work)
     cudaStream_t side = nullptr;
     std::vector<cudaEvent_t> fork_events;
     cudaEvent_t join_event = nullptr;
-    bool side_wgrad = true;           // LD_TRAIN_SIDE=0: everything on the caller's stream
+    bool side_wgrad = false;          // LD_TRAIN_SIDE=1 enables it.  Measured: 5.08-5.11 ms per step against 4.90-5.03 ms with everything on
+                                      // the caller's stream (same box, CUDA graph): the persistent weight-gradient CTAs take the SMs from the
+                                      // element-wise kernels instead of sharing them -- off by default
     void* pack_items = nullptr;       // device table of the weight slabs pack_all_kernel writes every step
     int n_pack_items = 0;
     float *x_keep = nullptr, *mask1_keep = nullptr, *mask2_keep = nullptr, *params_keep = nullptr;   // inputs of the last forward
