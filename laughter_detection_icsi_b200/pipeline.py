@@ -77,7 +77,9 @@ class LaughterPipeline:
             if not hasattr(self, "_pool"):
                 from concurrent.futures import ThreadPoolExecutor
                 import os
-                self._pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
+                # one process per GPU shares the host cores with its siblings (torchrun sets LOCAL_WORLD_SIZE)
+                siblings = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+                self._pool = ThreadPoolExecutor(max_workers=max(2, min(16, (os.cpu_count() or 1) // siblings)))
             results = list(self._pool.map(one, work))
         else:
             results = [one(w) for w in work]
