@@ -106,107 +106,125 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackItem* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ stem
+// Both stem kernels walk the image like the element-wise BatchNorm kernels (EwWalk, below): a warp owns one 8-channel chunk for
+// good and visits groups of 32 consecutive real pixels, so per-channel sums stay in registers until one reduction at the end.
+struct StemWalk {   // (a copy of EwWalk's arithmetic; EwWalk is declared further down)
+    int kc, lane, P, W, H;
+    unsigned group, group_stride, n_groups, magic_w, magic_h;
+    __device__ StemWalk(int B, int H_, int W_) : W(W_), H(H_) {
+        const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+        lane = threadIdx.x & 31;
+        kc = static_cast<int>(warp % 8);
+        group = warp / 8;
+        group_stride = n_warps / 8;   // the launchers keep n_warps a multiple of 8
+        P = B * H * W;
+        n_groups = (static_cast<unsigned>(P) + 31u) / 32u;
+        magic_w = 0xFFFFFFFFu / static_cast<unsigned>(W) + 1u;
+        magic_h = 0xFFFFFFFFu / static_cast<unsigned>(H) + 1u;
+    }
+    __device__ bool pixel(unsigned g, int& b, int& r0, int& c0) const {
+        const unsigned pix = g * 32u + lane;
+        const unsigned row = __umulhi(pix, magic_w);
+        c0 = static_cast<int>(pix - row * W);
+        b = static_cast<int>(__umulhi(row, magic_h));
+        r0 = static_cast<int>(row - b * H);
+        return pix < static_cast<unsigned>(P);
+    }
+};
+__device__ __forceinline__ void stem_patch(const float* __restrict__ x, int b, int r0, int c0, int H, int W, float (&in)[9]) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int r = r0 + ky - 1, c = c0 + kx - 1;
+            in[ky * 3 + kx] = (r >= 0 && r < H && c >= 0 && c < W) ? __ldg(x + (static_cast<long long>(b) * H + r) * W + c) : 0.f;
+        }
+}
+
 // conv1 (1 -> 64, 3x3, pad 1, no bias) on the fp32 features: raw output z0 (bf16, plain) + channel sums.
 __global__ void __launch_bounds__(256)
 stem_fwd_kernel(const float* __restrict__ x, int B, int H, int W, const float* __restrict__ w /*[64][9]*/, TPlane z,
                 float* __restrict__ stats /*[128]*/) {
-    __shared__ float s_w[64 * 9];
     __shared__ float s_acc[128];
-    for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) s_w[i] = w[i];
     for (int i = threadIdx.x; i < 128; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
-    const long long n = static_cast<long long>(B) * H * W;
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const bool live = i < n;
-    float v[64];
+    const StemWalk wk(B, H, W);
+    const int kc = wk.kc;
+    float wt[8][9], sum[8], sq[8];
 #pragma unroll
-    for (int c = 0; c < 64; ++c) v[c] = 0.f;
-    if (live) {
-        const int c0 = static_cast<int>(i % W), r0 = static_cast<int>((i / W) % H), b = static_cast<int>(i / (static_cast<long long>(W) * H));
-        float in[9];
+    for (int e = 0; e < 8; ++e) {
+        sum[e] = 0.f; sq[e] = 0.f;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+        for (int t = 0; t < 9; ++t) wt[e][t] = w[(kc * 8 + e) * 9 + t];
+    }
+    for (unsigned g = wk.group; g < wk.n_groups; g += wk.group_stride) {
+        int b, r0, c0;
+        if (!wk.pixel(g, b, r0, c0)) continue;
+        float in[9], o[8];
+        stem_patch(x, b, r0, c0, H, W, in);
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int r = r0 + ky - 1, c = c0 + kx - 1;
-                in[ky * 3 + kx] = (r >= 0 && r < H && c >= 0 && c < W) ? __ldg(x + (static_cast<long long>(b) * H + r) * W + c) : 0.f;
-            }
-#pragma unroll
-        for (int ch = 0; ch < 64; ++ch) {
+        for (int e = 0; e < 8; ++e) {
             float a = 0.f;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) a = fmaf(s_w[ch * 9 + t], in[t], a);
-            v[ch] = a;
+            for (int t = 0; t < 9; ++t) a = fmaf(wt[e][t], in[t], a);
+            o[e] = a;
+            sum[e] += a;
+            sq[e] = fmaf(a, a, sq[e]);
         }
-        int which;
-        const long long p = tpix(z, b, r0, c0, which);
+        store8(z.base[0] + kc * z.kc_stride + static_cast<long long>((b * z.hp + 1 + r0) * z.wp + 1 + c0) * 8, o);
+    }
 #pragma unroll
-        for (int kc = 0; kc < 8; ++kc) {
-            float o[8];
+    for (int e = 0; e < 8; ++e) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = v[kc * 8 + e];
-            store8(z.base[0] + kc * z.kc_stride + p * 8, o);
+        for (int o = 16; o >= 1; o >>= 1) {
+            sum[e] += __shfl_xor_sync(0xffffffffu, sum[e], o);
+            sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], o);
         }
     }
-    const int lane = threadIdx.x & 31;
-    float q[64];
+    if (wk.lane == 0) {
 #pragma unroll
-    for (int c = 0; c < 64; ++c) q[c] = v[c] * v[c];
-    warp_reduce_channels<64>(v, lane);
-    warp_reduce_channels<64>(q, lane);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int c = warp_reduce_channel_of(lane, k, 64);
-        atomicAdd(s_acc + c, v[k]);
-        atomicAdd(s_acc + 64 + c, q[k]);
+        for (int e = 0; e < 8; ++e) {
+            atomicAdd(s_acc + kc * 8 + e, sum[e]);
+            atomicAdd(s_acc + 64 + kc * 8 + e, sq[e]);
+        }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < 128; k += blockDim.x) atomicAdd(stats + k, s_acc[k]);
 }
 
-// dW conv1 [64][9] = sum_p dz0[p][ch] * x(p + tap)
+// dW conv1 [64][9] = sum_p dz0[p][ch] * x(p + tap): 8 channels x 9 taps of partial sums per thread, reduced once at the end.
 __global__ void __launch_bounds__(256)
 stem_wgrad_kernel(const float* __restrict__ x, int B, int H, int W, TPlane dz, float* __restrict__ dw /*[64][9]*/) {
     __shared__ float s_acc[64 * 9];
     for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
-    const long long n = static_cast<long long>(B) * H * W;
-    const int lane = threadIdx.x & 31;
-    for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x; base < n; base += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long i = base + threadIdx.x;
-        float in[9], g[64];
+    const StemWalk wk(B, H, W);
+    const int kc = wk.kc;
+    float acc[8][9];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) in[t] = 0.f;
+    for (int e = 0; e < 8; ++e)
 #pragma unroll
-        for (int c = 0; c < 64; ++c) g[c] = 0.f;
-        if (i < n) {
-            const int c0 = static_cast<int>(i % W), r0 = static_cast<int>((i / W) % H), b = static_cast<int>(i / (static_cast<long long>(W) * H));
+        for (int t = 0; t < 9; ++t) acc[e][t] = 0.f;
+    for (unsigned g = wk.group; g < wk.n_groups; g += wk.group_stride) {
+        int b, r0, c0;
+        if (!wk.pixel(g, b, r0, c0)) continue;
+        float in[9], gz[8];
+        stem_patch(x, b, r0, c0, H, W, in);
+        load8(dz.base[0] + kc * dz.kc_stride + static_cast<long long>((b * dz.hp + 1 + r0) * dz.wp + 1 + c0) * 8, gz);
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+        for (int e = 0; e < 8; ++e)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int r = r0 + ky - 1, c = c0 + kx - 1;
-                    in[ky * 3 + kx] = (r >= 0 && r < H && c >= 0 && c < W) ? __ldg(x + (static_cast<long long>(b) * H + r) * W + c) : 0.f;
-                }
-            int which;
-            const long long p = tpix(dz, b, r0, c0, which);
-#pragma unroll
-            for (int kc = 0; kc < 8; ++kc) {
-                float o[8];
-                load8(dz.base[0] + kc * dz.kc_stride + p * 8, o);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) g[kc * 8 + e] = o[e];
-            }
-        }
-        for (int t = 0; t < 9; ++t) {
-            float prod[64];
-#pragma unroll
-            for (int c = 0; c < 64; ++c) prod[c] = g[c] * in[t];
-            warp_reduce_channels<64>(prod, lane);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) atomicAdd(s_acc + warp_reduce_channel_of(lane, k, 64) * 9 + t, prod[k]);
-        }
+            for (int t = 0; t < 9; ++t) acc[e][t] = fmaf(gz[e], in[t], acc[e][t]);
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            float v = acc[e][t];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (wk.lane == 0) atomicAdd(s_acc + (kc * 8 + e) * 9 + t, v);
+        }
     __syncthreads();
     for (int k = threadIdx.x; k < 64 * 9; k += blockDim.x) atomicAdd(dw + k, s_acc[k]);
 }
@@ -1321,7 +1339,7 @@ cudaError_t train_forward(TrainNet* n, const float* params, const float* x, int 
     {
         ConvHost& c = n->convs[0];
         c.bn.count = static_cast<long long>(B) * n->cfg.H * n->cfg.W;
-        stem_fwd_kernel<<<blocks_for(c.bn.count, 256), 256, 0, stream>>>(x, B, n->cfg.H, n->cfg.W, params + c.w_off, c.z, n->stats + c.bn.fwd_sums);
+        stem_fwd_kernel<<<ew_grid(n, c.bn.count * 8), 256, 0, stream>>>(x, B, n->cfg.H, n->cfg.W, params + c.w_off, c.z, n->stats + c.bn.fwd_sums);
         const long long work = c.bn.count * 8;
         bn_apply_kernel<<<ew_grid(n, work), 256, 0, stream>>>(c.z, bn_ref(*n, c.bn), 1, 0, c.z, bn_ref(*n, c.bn), n->levels[0], B);
         n->launches += 2;
@@ -1587,7 +1605,7 @@ cudaError_t train_backward(TrainNet* n, const float* dprobs, float* grads, cudaS
     {   // stem
         ConvHost& c = n->convs[0];
         bn_backward(n->dlevels[0], n->levels[0], 2, c, 0, c.dz);
-        stem_wgrad_kernel<<<n->num_sms * 4, 256, 0, fork_side()>>>(n->x_d, B, n->cfg.H, n->cfg.W, c.dz, grads + c.w_off);
+        stem_wgrad_kernel<<<n->num_sms * 8, 256, 0, fork_side()>>>(n->x_d, B, n->cfg.H, n->cfg.W, c.dz, grads + c.w_off);
         ++n->launches;
     }
     LD_TRY(cudaGetLastError());
