@@ -36,13 +36,18 @@ __device__ __forceinline__ int find_channel(const ChannelTable& ct, long long s,
 // bytes of a plane.  The three kernel-row partial sums s_ky stay apart: every stem plane (interior: s0 + s1 + s2; top edge
 // of a window: s1 + s2; bottom edge: s0 + s1, 99 rows up) is a masked sum of them, so the 3 x 3 taps are multiplied once
 // for all planes (9 instead of 21 multiply-adds per pixel and channel) and the feature patch is read once.
-template <int kStemPx>
+// The BatchNorm scale is folded into the fp32 weights when they are staged and the shift starts the ky = 1 partial sum, so a
+// plane costs one or two additions per channel; the ReLU runs on the packed fp16 pair (max commutes with the rounding).
+// kFixed: the launch has exactly the three planes of a window taller than two rows, in the planner's order -- top edge
+// (ky = 1, 2), bottom edge (ky = 0, 1), interior (all) -- and the masked sums are compile-time: (s1 + s2), (s0 + s1) and
+// (s0 + s1) + s2.  Any other plane set runs the generic instantiation with run-time masks.
+template <int kStemPx, bool kFixed>
 __global__ void __launch_bounds__(256)
 stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long long chunk_row0, int rows, int row_lo, int rows_total) {
-    __shared__ float s_w[64 * 9];
-    __shared__ float s_scale[64], s_shift[64];
-    for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) s_w[i] = L.w[i];
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) { s_scale[i] = L.scale[i]; s_shift[i] = L.shift[i]; }
+    __shared__ __align__(16) float s_w[64 * 9];
+    __shared__ __align__(16) float s_shift[64];
+    for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) s_w[i] = L.w[i] * L.scale[i / 9];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_shift[i] = L.shift[i];
     __syncthreads();
 
     const int wp = L.W + 2;
@@ -51,10 +56,12 @@ stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long
     const int lane = threadIdx.x & 31;
     const long long base = warp * (32 * kStemPx);
     if (base >= n_pix) return;
+    constexpr int kJobs = kFixed ? 3 : kMaxStemJobs;
 
     // per pixel: the 3 x 3 feature patch (real column = padded column - 1) and where it lands in each plane
     float x[kStemPx][3][3];
-    long long dst[kStemPx][kMaxStemJobs];   // element offset of the pixel inside plane j, or -1
+    long long dst[kStemPx][kJobs];   // element offset of the pixel inside plane j
+    bool ok[kStemPx][kJobs];         // ... and whether the plane has that row
     bool pad[kStemPx];
 #pragma unroll
     for (int i = 0; i < kStemPx; ++i) {
@@ -76,50 +83,78 @@ stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long
             }
         }
 #pragma unroll
-        for (int j = 0; j < kMaxStemJobs; ++j) {
+        for (int j = 0; j < kJobs; ++j) {
             const int r = G - (j < L.n_jobs ? L.jobs[j].row_shift : 0);
-            dst[i][j] = (live && j < L.n_jobs && r >= 0 && r < rows) ? (static_cast<long long>(r) * wp + pc) * 8 : -1;
+            ok[i][j] = live && j < L.n_jobs && r >= 0 && r < rows;
+            dst[i][j] = (static_cast<long long>(r) * wp + pc) * 8;
         }
     }
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    const __half2 zero = __floats2half2_rn(0.f, 0.f);
+    auto pack_relu = [&](const float (&o)[8]) {
+        uint4 ov;
+        __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oh[e] = __hmax2(__floats2half2_rn(o[2 * e], o[2 * e + 1]), zero);
+        return ov;
+    };
+#pragma unroll 1
     for (int kc = 0; kc < 8; ++kc) {
         float part[3][kStemPx][8];
+        // the 72 weights and 8 shifts of this channel chunk: warp-uniform 16-byte shared-memory reads
+        float w[8][9], sh[8];
+        {
+            const float4* w4 = reinterpret_cast<const float4*>(s_w + kc * 72);
+            float* wf = &w[0][0];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int ch = kc * 8 + e;
-            float w[9];
+            for (int q = 0; q < 18; ++q) {
+                const float4 v = w4[q];
+                wf[4 * q] = v.x; wf[4 * q + 1] = v.y; wf[4 * q + 2] = v.z; wf[4 * q + 3] = v.w;
+            }
+            const float4 s0 = *reinterpret_cast<const float4*>(s_shift + kc * 8), s1 = *reinterpret_cast<const float4*>(s_shift + kc * 8 + 4);
+            sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
+        }
 #pragma unroll
-            for (int t = 0; t < 9; ++t) w[t] = s_w[ch * 9 + t];
+        for (int e = 0; e < 8; ++e)
 #pragma unroll
             for (int i = 0; i < kStemPx; ++i)
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
-                    float a = 0.f;
+                    float a = ky == 1 ? sh[e] : 0.f;   // the ky = 1 partial sum carries the shift
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) a = fmaf(w[ky * 3 + kx], x[i][ky][kx], a);
+                    for (int kx = 0; kx < 3; ++kx) a = fmaf(w[e][ky * 3 + kx], x[i][ky][kx], a);
                     part[ky][i][e] = a;
                 }
-        }
 #pragma unroll
-        for (int j = 0; j < kMaxStemJobs; ++j) {
-            if (j >= L.n_jobs) continue;
-            const StemJob job = L.jobs[j];
-#pragma unroll
-            for (int i = 0; i < kStemPx; ++i) {
-                if (dst[i][j] < 0) continue;
-                float o[8];
+        for (int i = 0; i < kStemPx; ++i) {
+            if constexpr (kFixed) {
+                float o12[8], o01[8], o012[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    float a = 0.f;   // ky ascending over the kernel rows the plane sees
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-                        if ((job.mask >> ky) & 1) a += part[ky][i][e];
-                    o[e] = fmaxf(fmaf(a, s_scale[kc * 8 + e], s_shift[kc * 8 + e]), 0.f);
+                    o12[e] = part[1][i][e] + part[2][i][e];
+                    o01[e] = part[0][i][e] + part[1][i][e];
+                    o012[e] = o01[e] + part[2][i][e];
                 }
-                uint4 ov;
-                __half2* oh = reinterpret_cast<__half2*>(&ov);
+                const uint4 v0 = pad[i] ? zero4 : pack_relu(o12), v1 = pad[i] ? zero4 : pack_relu(o01), v2 = pad[i] ? zero4 : pack_relu(o012);
+                if (ok[i][0]) *reinterpret_cast<uint4*>(L.jobs[0].out + dst[i][0] + kc * L.jobs[0].kc_stride) = v0;
+                if (ok[i][1]) *reinterpret_cast<uint4*>(L.jobs[1].out + dst[i][1] + kc * L.jobs[1].kc_stride) = v1;
+                if (ok[i][2]) *reinterpret_cast<uint4*>(L.jobs[2].out + dst[i][2] + kc * L.jobs[2].kc_stride) = v2;
+            } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) oh[e] = pad[i] ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(o[2 * e], o[2 * e + 1]);
-                *reinterpret_cast<uint4*>(job.out + dst[i][j] + kc * job.kc_stride) = ov;
+                for (int j = 0; j < kJobs; ++j) {
+                    if (j >= L.n_jobs) continue;
+                    const StemJob job = L.jobs[j];
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float a = (job.mask & 2) ? part[1][i][e] : sh[e];
+                        if (job.mask & 1) a += part[0][i][e];
+                        if (job.mask & 4) a += part[2][i][e];
+                        o[e] = a;
+                    }
+                    const uint4 ov = pad[i] ? zero4 : pack_relu(o);
+                    if (ok[i][j]) *reinterpret_cast<uint4*>(job.out + dst[i][j] + kc * job.kc_stride) = ov;
+                }
             }
         }
     }
@@ -202,11 +237,15 @@ cudaError_t launch_stem(const StemLaunch& L, const ChannelTable& ct, const float
     for (int j = 0; j < L.n_jobs; ++j) { lo = j == 0 ? L.jobs[j].row_shift : (L.jobs[j].row_shift < lo ? L.jobs[j].row_shift : lo); hi = L.jobs[j].row_shift > hi ? L.jobs[j].row_shift : hi; }
     const int rows_total = rows + hi - lo;
     // pixels per thread: 2 keeps the kernel under 128 registers (two CTAs per SM), 4 reuses every weight fetch twice as often
-    static const int px = []() { const char* v = std::getenv("LD_STEM_PX"); return (v && std::atoi(v) == 4) ? 4 : 2; }();
+    static const int px_env = []() { const char* v = std::getenv("LD_STEM_PX"); return (v && std::atoi(v) == 4) ? 4 : 2; }();
+    const bool fixed0 = L.n_jobs == 3 && L.jobs[0].mask == 6 && L.jobs[1].mask == 3 && L.jobs[2].mask == 7;
+    const int px = fixed0 ? px_env : 2;
     const long long threads = (static_cast<long long>(rows_total) * (L.W + 2) + px - 1) / px;   // 32 * px pixels per warp
     const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
-    if (px == 4) stem_kernel<4><<<grid, 256, 0, stream>>>(L, ct, feats, chunk_row0, rows, lo, rows_total);
-    else stem_kernel<2><<<grid, 256, 0, stream>>>(L, ct, feats, chunk_row0, rows, lo, rows_total);
+    const bool fixed = L.n_jobs == 3 && L.jobs[0].mask == 6 && L.jobs[1].mask == 3 && L.jobs[2].mask == 7;
+    if (!fixed) stem_kernel<2, false><<<grid, 256, 0, stream>>>(L, ct, feats, chunk_row0, rows, lo, rows_total);
+    else if (px == 4) stem_kernel<4, true><<<grid, 256, 0, stream>>>(L, ct, feats, chunk_row0, rows, lo, rows_total);
+    else stem_kernel<2, true><<<grid, 256, 0, stream>>>(L, ct, feats, chunk_row0, rows, lo, rows_total);
     return cudaGetLastError();
 }
 
