@@ -222,6 +222,21 @@ LD_API int32_t ld_timing_read_convs(ld_ctx* ctx, double* out_ms, int32_t cap, in
  * producer wait, MMA wait-operands, MMA wait-accumulator, MMA issue, epilogue wait, epilogue work, CTA lifetime, tiles.
  * Returns the number of conv launches (0 when the counters are off). */
 LD_API int32_t ld_debug_gemm_counters(ld_ctx* ctx, uint64_t* out, int32_t cap_convs, int32_t reset);
+/* Debug (LD_GEMM_PROF=1): cycles producer warp 0 of every conv launch spent waiting for the neighbouring layers of its
+ * layer-pipelined launch, summed over CTAs, in units of 1024 cycles: low 32 bits all waits (dataflow + back-pressure), high
+ * 32 bits the dataflow share; read before ld_debug_gemm_counters resets. */
+LD_API int32_t ld_debug_gemm_sync_wait(ld_ctx* ctx, uint64_t* out, int32_t cap_convs);
+/* Debug (LD_GEMM_PROF=1): per conv launch, the smallest and the largest CTA lifetime per tile (cycles) seen among the CTAs of
+ * its launches since the last reset -- how far the persistent CTAs of a launch drift apart; read before ld_debug_gemm_counters
+ * resets. */
+LD_API int32_t ld_debug_gemm_cta_spread(ld_ctx* ctx, double* min_cycles_per_tile, double* max_cycles_per_tile, int32_t cap_convs);
+/* Layer-pipelined conv launches: consecutive conv launches of one shape (cin, cout) and resolution run as the roles of ONE
+ * kernel launch, each on its own share of the SMs, and hand their output tiles over through L2 (replaces the per-layer
+ * launches of the loop at reference models.py:222-228).  Per conv launch of the plan (order of
+ * ld_plan_json's "convs"): its group (-1: launched on its own) and the CTAs its role gets.  Returns the number of conv
+ * launches.  Environment at context creation: LD_GEMM_PIPE = 0 (off, default: measured no faster than separate launches) /
+ * 1 (cout >= 48 only) / 2 (all). */
+LD_API int32_t ld_conv_pipeline_groups(ld_ctx* ctx, int32_t* group_of_conv, int32_t* ctas_of_conv, int32_t cap_convs);
 
 #ifdef __cplusplus
 }

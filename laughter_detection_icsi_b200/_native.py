@@ -85,6 +85,9 @@ SIGNATURES = {
     "ld_train_debug_read": (c_int64, [c_void_p, c_int32, c_int32, c_void_p, POINTER(c_int32)]),
     "ld_train_debug_checksums": (c_int32, [c_void_p, POINTER(c_double), c_int32]),
     "ld_debug_gemm_counters": (c_int32, [c_void_p, POINTER(ctypes.c_uint64), c_int32, c_int32]),
+    "ld_debug_gemm_sync_wait": (c_int32, [c_void_p, POINTER(ctypes.c_uint64), c_int32]),
+    "ld_debug_gemm_cta_spread": (c_int32, [c_void_p, POINTER(c_double), POINTER(c_double), c_int32]),
+    "ld_conv_pipeline_groups": (c_int32, [c_void_p, POINTER(c_int32), POINTER(c_int32), c_int32]),
 }
 
 _lib = None
@@ -137,21 +140,28 @@ def plan_json(cfg=None):
     return json.loads(buf.value.decode())
 
 
-def plan_plane_bytes_per_row(cfg=None, conv=None):
+def plan_plane_bytes_per_row(cfg=None, conv=None, groups=None):
     """Activation bytes the conv launches of the streaming plan move per sequence row if every plane crosses HBM once per
     launch that touches it: for each launch its distinct input, residual and output planes (fp16, wp x C per row).  This is
     the algorithmic traffic figure behind bench.py's HBM roofline.  `conv` restricts the sum to the
-    launches of one conv layer (e.g. "block1.1.conv2")."""
+    launches of one conv layer (e.g. "block1.1.conv2").  `groups` (per conv: id of its layer-pipelined group or -1, see
+    Engine.conv_pipeline_groups) makes the convs of a group ONE launch: a plane written by one role and read by the next
+    is handed over through L2 and counts once."""
     plan = plan_json(cfg)
     size = {p["id"]: 2 * p["wp"] * p["C"] * (2 if p.get("split") else 1) for p in plan["planes"]}   # [hi | lo] planes count twice
     total = 0
-    for c in plan["convs"]:
+    touched_of_group = {}
+    for i, c in enumerate(plan["convs"]):
         if conv is not None and c["conv"] != conv:
             continue
-        touched = set()
+        g = groups[i] if (groups is not None and conv is None and i < len(groups)) else -1
+        touched = touched_of_group.setdefault(g, set()) if g >= 0 else set()
         for job in c["jobs"]:
             touched.update(p for p, _, _ in job["taps"])
             touched.update(x for x in (job["res"], job["out0"], job.get("out1", -1)) if x >= 0)
+        if g < 0:
+            total += sum(size[i] for i in touched)
+    for touched in touched_of_group.values():
         total += sum(size[i] for i in touched)
     return float(total)
 

@@ -52,6 +52,8 @@ struct ConvWeights {
     std::string conv, bn;
 };
 
+constexpr int kProfSlots = 16;   // cycle counters per conv launch (LD_GEMM_PROF=1; ld_debug_gemm_counters reports the first 8)
+
 struct ConvLaunchDev {
     ld::GemmLaunch h;   // parameters (passed to the kernel by value, __grid_constant__) + the job table
     int wp = 0;
@@ -124,7 +126,16 @@ struct ld_ctx {
     uint8_t* workspace = nullptr;
     size_t workspace_bytes = 0;
     ld::TrainNet* train = nullptr;   // training network (ld_train_create)
-    unsigned long long* gemm_prof = nullptr;  // LD_GEMM_PROF=1: 8 cycle counters per conv launch
+    unsigned long long* gemm_prof = nullptr;  // LD_GEMM_PROF=1: kProfSlots cycle counters per conv launch
+    // layer-pipelined conv launches (ld_types.h, GemmMultiParams): groups of consecutive conv launches of one shape
+    struct PipeGroup { std::vector<int> convs; int ctas[ld::kMaxRoles] = {0, 0, 0, 0}; };
+    std::vector<PipeGroup> pipe_groups;
+    std::vector<int> conv_group;      // per conv launch: its group, or -1
+    unsigned* pipe_done[2] = {nullptr, nullptr};   // completion counters, used alternately by successive pipelined launches
+    int pipe_m_cap = 0;
+    long long pipe_launches = 0;
+    int pipe_lead_max = 256;
+    int pipe_dbg = 0;
     std::vector<PlaneDev> planes;
     std::map<std::string, ConvWeights> weights;
     std::vector<ConvLaunchDev> convs;
@@ -450,8 +461,8 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
     // ---- launch tables -----------------------------------------------------------------------------------
     const ld::GemmTuning tune = ld::gemm_tuning_from_env();
     if (std::getenv("LD_GEMM_PROF") && std::atoi(std::getenv("LD_GEMM_PROF"))) {
-        LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->gemm_prof), plan.convs.size() * 8 * sizeof(unsigned long long)));
-        LD_CUDA_C(cudaMemset(ctx->gemm_prof, 0, plan.convs.size() * 8 * sizeof(unsigned long long)));
+        LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->gemm_prof), plan.convs.size() * kProfSlots * sizeof(unsigned long long)));
+        LD_CUDA_C(cudaMemset(ctx->gemm_prof, 0, plan.convs.size() * kProfSlots * sizeof(unsigned long long)));
     }
     ctx->convs.resize(plan.convs.size());
     for (size_t li = 0; li < plan.convs.size(); ++li) {
@@ -467,7 +478,7 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         L.w_stack = cs.ksize == 3 ? 1 : 0;
         L.w_blocks = cs.ksize == 3 ? (w.split_w ? 2 : 1) : 0;
         L.split_out = cs.split_out;
-        L.prof = ctx->gemm_prof ? ctx->gemm_prof + 8 * li : nullptr;
+        L.prof = ctx->gemm_prof ? ctx->gemm_prof + kProfSlots * li : nullptr;
         cd.wp = cs.wp;
         std::vector<ld::HostJob> jobs(cs.jobs.size());
         for (size_t j = 0; j < cs.jobs.size(); ++j) {
@@ -493,6 +504,116 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         }
         std::string err;
         if (!ld::gemm_build_launch(L, jobs, tune, err)) return cleanup_fail(fail(LD_ERR_INVALID, "conv " + cs.conv + ": " + err));
+    }
+    // ---- layer-pipelined launches: consecutive conv launches of one shape and resolution become the roles of ONE launch whose
+    // CTAs hand their tiles over through L2.  LD_GEMM_PIPE: 0 off (default), 1 only the cout >= 48 layers, 2 all.
+    {
+        const char* v = std::getenv("LD_GEMM_PIPE");
+        const int mode = v ? std::atoi(v) : 0;   // off by default: measured at best equal to the separate launches
+        const char* lm = std::getenv("LD_GEMM_PIPE_LEAD");
+        if (lm && std::atoi(lm) > 40) ctx->pipe_lead_max = std::atoi(lm);
+        {   // knock-out timing experiments produce garbage results: honoured only together with the profiling switch
+            const char* d = std::getenv("LD_GEMM_PIPE_DBG");
+            const char* pr = std::getenv("LD_GEMM_PROF");
+            ctx->pipe_dbg = (d && pr && std::atoi(pr)) ? std::atoi(d) : 0;
+        }
+        const char* mr = std::getenv("LD_GEMM_PIPE_ROLES");
+        const int max_roles = (mr && std::atoi(mr) >= 2 && std::atoi(mr) <= ld::kMaxRoles) ? std::atoi(mr) : ld::kMaxRoles;
+        ctx->conv_group.assign(plan.convs.size(), -1);
+        auto pipe_shape = [](const ld::GemmLaunch& L) {
+            return (L.cin == 64 && L.cout == 64) || (L.cin == 32 && L.cout == 32) || (L.cin == 16 && L.cout == 16) ||
+                   (L.cin == 64 && L.cout == 32) || (L.cin == 32 && L.cout == 16);
+        };
+        for (size_t li = 0; mode > 0 && li < plan.convs.size();) {
+            size_t e = li + 1;
+            const ld::GemmLaunch& A = ctx->convs[li].h;
+            while (e < plan.convs.size() && e - li < static_cast<size_t>(max_roles)) {
+                const ld::GemmLaunch& P = ctx->convs[e - 1].h;
+                const ld::GemmLaunch& B = ctx->convs[e].h;
+                if (B.cin != A.cin || B.cout != A.cout || B.tmem_cols != A.tmem_cols || B.wp != A.wp || B.hp != A.hp ||
+                    P.out_mode != ld::OUT_PLAIN)
+                    break;
+                ++e;
+            }
+            if (e - li >= 2 && pipe_shape(A) && (mode >= 2 || A.cout >= 48)) {
+                ld_ctx::PipeGroup g;
+                for (size_t k = li; k < e; ++k) { g.convs.push_back(static_cast<int>(k)); ctx->conv_group[k] = static_cast<int>(ctx->pipe_groups.size()); }
+                ctx->pipe_groups.push_back(g);
+            }
+            li = e;
+        }
+        // LD_GEMM_PIPE_W: comma-separated relative cost per conv launch (plan order), overriding the tap-count model below
+        std::vector<double> w_env;
+        if (const char* we = std::getenv("LD_GEMM_PIPE_W")) {
+            std::string t(we);
+            size_t pos = 0;
+            while (pos < t.size()) {
+                const size_t c = t.find(',', pos);
+                w_env.push_back(std::atof(t.substr(pos, c == std::string::npos ? std::string::npos : c - pos).c_str()));
+                if (c == std::string::npos) break;
+                pos = c + 1;
+            }
+        }
+        for (auto& g : ctx->pipe_groups) {
+            const int n_roles = static_cast<int>(g.convs.size());
+            // dataflow: which planes does each role write, and up to which pixel does every job of the later roles read them
+            for (int r = 1; r < n_roles; ++r) {
+                ld::GemmLaunch& L = ctx->convs[g.convs[r]].h;
+                for (int j = 0; j < L.n_jobs; ++j) {
+                    ld::GemmJob& job = L.jobs[j];
+                    for (int gi = 0; gi < job.n_groups; ++gi)
+                        for (int back = 0; back < 3 && r - 1 - back >= 0; ++back) {
+                            const ld::GemmLaunch& U = ctx->convs[g.convs[r - 1 - back]].h;
+                            bool hit = false;
+                            for (int uj = 0; uj < U.n_jobs && !hit; ++uj)
+                                for (int o = 0; o < U.jobs[uj].n_outs && !hit; ++o)
+                                    hit = U.jobs[uj].outs[o].out0 == job.groups[gi].src || (U.jobs[uj].outs[o].out1 != nullptr && U.jobs[uj].outs[o].out1 == job.groups[gi].src);
+                            if (hit) job.dep_back[back] = std::max(job.dep_back[back], job.groups[gi].shift + L.ext_alloc - 1);
+                        }
+                }
+            }
+            // CTAs per role in proportion to the work: accumulator columns x K steps over the tap programs (the tensor-pipe time)
+            // plus the outputs the epilogue stores
+            const int total = ctx->num_sms * (ctx->convs[g.convs[0]].h.tmem_cols == 256 ? 2 : 1);
+            double w[ld::kMaxRoles] = {0, 0, 0, 0}, w_sum = 0;
+            for (int r = 0; r < n_roles; ++r) {
+                const ld::GemmLaunch& L = ctx->convs[g.convs[r]].h;
+                if (static_cast<size_t>(g.convs[r]) < w_env.size() && w_env[g.convs[r]] > 0) {
+                    w[r] = w_env[g.convs[r]];
+                } else {
+                    // least-squares fit of the stand-alone launch times of the 19 layers of resnet_base (profiles/r02): tensor-pipe
+                    // columns x K steps, stored output channels, loaded input channels, MMA taps (issue overhead)
+                    for (int j = 0; j < L.n_jobs; ++j) {
+                        const uint4* tp = L.job_tapw(j);
+                        for (int t = 0; t < L.job_taps[j].n_taps; ++t) {
+                            const int ncols = static_cast<int>((tp[t].w >> 17) & 63) * 8;
+                            w[r] += std::max(ncols, 64) * (L.cin / 16) * ((tp[t].x & ld::kTapHalfK) ? 0.5 : 1.0) + 95.0;
+                        }
+                        // (roles behind the first find their inputs in L2: measured busy time per tile, profiles/r02/gemm_pipeline_experiment.log)
+                        w[r] += 23.3 * L.jobs[j].n_outs * L.cout + (r == 0 ? 1.0 : 0.77) * 25.6 * L.jobs[j].n_groups * L.cin;
+                    }
+                }
+                w_sum += w[r];
+            }
+            int used = 0, big = 0;
+            for (int r = 0; r < n_roles; ++r) {
+                g.ctas[r] = std::max(1, static_cast<int>(total * w[r] / w_sum + 0.5));
+                used += g.ctas[r];
+                if (g.ctas[r] > g.ctas[big]) big = r;
+            }
+            g.ctas[big] += total - used;
+            if (g.ctas[big] < 1) return cleanup_fail(fail(LD_ERR_INVALID, "pipelined launch: CTA split failed"));
+        }
+        if (!ctx->pipe_groups.empty()) {
+            int wp_min = 1 << 30;
+            for (const auto& cd : ctx->convs) wp_min = std::min(wp_min, cd.wp);
+            ctx->pipe_m_cap = (ctx->rows_alloc * 64 + ld::kTileM - 1) / ld::kTileM + 1;   // wp <= 64
+            for (int b = 0; b < 2; ++b) {
+                const size_t bytes = static_cast<size_t>(ld::kMaxRoles) * ctx->pipe_m_cap * sizeof(unsigned);
+                LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&ctx->pipe_done[b]), bytes));
+                LD_CUDA_C(cudaMemset(ctx->pipe_done[b], 0, bytes));
+            }
+        }
     }
     // stem
     ctx->stem.n_jobs = static_cast<int>(plan.stem.size());
@@ -538,6 +659,7 @@ void ld_destroy(ld_ctx* ctx) {
     if (ctx->workspace) cudaFree(ctx->workspace);
     if (ctx->train) ld::train_destroy(ctx->train);
     if (ctx->gemm_prof) cudaFree(ctx->gemm_prof);
+    for (int b = 0; b < 2; ++b) if (ctx->pipe_done[b]) cudaFree(ctx->pipe_done[b]);
     for (auto& cd : ctx->convs) ld::gemm_release(cd.h);
     for (auto& kv : ctx->weights) {
         if (kv.second.w) cudaFree(kv.second.w);
@@ -653,6 +775,23 @@ int ld_resnet_infer_windows(ld_ctx* ctx, const float* feats_d, const int64_t* ch
             auto& cd = ctx->convs[ci];
             const int M = rows * cd.wp;
             const int m_tiles = (M + ld::kTileM - 1) / ld::kTileM;
+            const int gi = ctx->conv_group.empty() ? -1 : ctx->conv_group[ci];
+            if (gi >= 0 && m_tiles <= ctx->pipe_m_cap) {   // a layer-pipelined group: one launch, timed under its first conv
+                const auto& g = ctx->pipe_groups[gi];
+                ld::GemmLaunch* roles[ld::kMaxRoles];
+                for (size_t r = 0; r < g.convs.size(); ++r) roles[r] = &ctx->convs[g.convs[r]].h;
+                ld::GemmSync sync;
+                sync.done = ctx->pipe_done[ctx->pipe_launches & 1];
+                sync.done_next = ctx->pipe_done[(ctx->pipe_launches + 1) & 1];
+                sync.m_cap = ctx->pipe_m_cap;
+                sync.lead_max = ctx->pipe_lead_max;
+                sync.dbg = ctx->pipe_dbg;
+                ++ctx->pipe_launches;
+                Timed t(ctx, stream, 0, 1, static_cast<int>(ci));
+                LD_CUDA(ld::launch_gemm_pipe(roles, static_cast<int>(g.convs.size()), g.ctas, sync, m_tiles, M, stream));
+                ci += g.convs.size() - 1;
+                continue;
+            }
             Timed t(ctx, stream, 0, 1, static_cast<int>(ci));
             LD_CUDA(ld::launch_gemm_taps(cd.h, m_tiles, M, ctx->num_sms, stream));
         }
@@ -1005,9 +1144,56 @@ int32_t ld_debug_gemm_counters(ld_ctx* ctx, uint64_t* out, int32_t cap_convs, in
     LD_CUDA(cudaSetDevice(ctx->device));
     LD_CUDA(cudaDeviceSynchronize());
     const int32_t n = std::min<int32_t>(static_cast<int32_t>(ctx->convs.size()), cap_convs);
-    LD_CUDA(cudaMemcpy(out, ctx->gemm_prof, static_cast<size_t>(n) * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    if (reset) LD_CUDA(cudaMemset(ctx->gemm_prof, 0, ctx->convs.size() * 8 * sizeof(unsigned long long)));
+    std::vector<uint64_t> all(ctx->convs.size() * kProfSlots);
+    LD_CUDA(cudaMemcpy(all.data(), ctx->gemm_prof, all.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    for (int32_t i = 0; i < n; ++i)
+        for (int k = 0; k < 8; ++k) out[i * 8 + k] = all[static_cast<size_t>(i) * kProfSlots + k];
+    if (reset) LD_CUDA(cudaMemset(ctx->gemm_prof, 0, all.size() * sizeof(unsigned long long)));
     return static_cast<int32_t>(ctx->convs.size());
+}
+
+int32_t ld_debug_gemm_sync_wait(ld_ctx* ctx, uint64_t* out, int32_t cap_convs) {
+    if (!ctx) return fail(LD_ERR_INVALID, "ctx is null");
+    if (!ctx->gemm_prof) return 0;
+    LD_CUDA(cudaSetDevice(ctx->device));
+    LD_CUDA(cudaDeviceSynchronize());
+    std::vector<uint64_t> all(ctx->convs.size() * kProfSlots);
+    LD_CUDA(cudaMemcpy(all.data(), ctx->gemm_prof, all.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    // low 32 bits: all waits in units of 1024 cycles; high 32 bits: the dataflow (upstream) share of them
+    for (int32_t i = 0; i < static_cast<int32_t>(ctx->convs.size()) && i < cap_convs; ++i)
+        out[i] = (all[static_cast<size_t>(i) * kProfSlots + 8] >> 10 & 0xFFFFFFFFull) | ((all[static_cast<size_t>(i) * kProfSlots + 9] >> 10) << 32);
+    return static_cast<int32_t>(ctx->convs.size());
+}
+
+int32_t ld_debug_gemm_cta_spread(ld_ctx* ctx, double* min_cycles_per_tile, double* max_cycles_per_tile, int32_t cap_convs) {
+    if (!ctx) return fail(LD_ERR_INVALID, "ctx is null");
+    if (!ctx->gemm_prof) return 0;
+    LD_CUDA(cudaSetDevice(ctx->device));
+    LD_CUDA(cudaDeviceSynchronize());
+    std::vector<uint64_t> all(ctx->convs.size() * kProfSlots);
+    LD_CUDA(cudaMemcpy(all.data(), ctx->gemm_prof, all.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    for (int32_t i = 0; i < static_cast<int32_t>(ctx->convs.size()) && i < cap_convs; ++i) {
+        const uint64_t mx = all[static_cast<size_t>(i) * kProfSlots + 10], inv = all[static_cast<size_t>(i) * kProfSlots + 11];
+        max_cycles_per_tile[i] = static_cast<double>(mx) / 1024.0;
+        min_cycles_per_tile[i] = inv ? static_cast<double>(~0ull - inv) / 1024.0 : 0.0;
+    }
+    return static_cast<int32_t>(ctx->convs.size());
+}
+
+int32_t ld_conv_pipeline_groups(ld_ctx* ctx, int32_t* group_of_conv, int32_t* ctas_of_conv, int32_t cap_convs) {
+    if (!ctx) return fail(LD_ERR_INVALID, "ctx is null");
+    const int32_t n = static_cast<int32_t>(ctx->convs.size());
+    for (int32_t i = 0; i < n && i < cap_convs; ++i) {
+        const int g = ctx->conv_group.empty() ? -1 : ctx->conv_group[i];
+        if (group_of_conv) group_of_conv[i] = g;
+        if (ctas_of_conv) {
+            ctas_of_conv[i] = 0;
+            if (g >= 0)
+                for (size_t r = 0; r < ctx->pipe_groups[g].convs.size(); ++r)
+                    if (ctx->pipe_groups[g].convs[r] == i) ctas_of_conv[i] = ctx->pipe_groups[g].ctas[r];
+        }
+    }
+    return n;
 }
 
 int32_t ld_timing_read_convs(ld_ctx* ctx, double* out_ms, int32_t cap, int32_t reset) {

@@ -41,6 +41,8 @@ constexpr int kIssuers = 4;      // MMA-issuing warps; a launch uses L.n_issuers
 constexpr int kProducers = 2;    // producer warps: with two rings each feeds half of the issuers
 constexpr int kEpiWarps = 8;      // epilogue warps: two per TMEM lane quadrant, each takes half of the channels of every output
 constexpr int kGemmThreads = 32 * (kProducers + kIssuers + kEpiWarps);
+constexpr int kPipeThreads = kGemmThreads + 64;   // layer-pipelined launches: one more warp sends the completion signals, another one
+                                                  // follows the completion counters of the neighbouring roles
 constexpr int kAccStages = kIssuers;  // barrier slots of the TMEM accumulator ring
 constexpr int kMaxStages = 16;
 constexpr int kTapBatch = 8;      // taps an issuer warp reads from the job table at a time
@@ -50,7 +52,8 @@ static_assert(kMaxTaps % kTapBatch == 0, "the tap table is read in whole batches
 //   0 producer: waiting for a free smem stage      1 MMA warp: waiting for operands      2 MMA warp: waiting for a free accumulator
 //   3 MMA warp: issuing                            4 epilogue warp 0: waiting for MMAs   5 epilogue warp 0: converting + storing
 //   6 CTA lifetime                                 7 tiles
-enum { PROF_PROD_WAIT = 0, PROF_MMA_WAIT_FULL, PROF_MMA_WAIT_ACC, PROF_MMA_ISSUE, PROF_EPI_WAIT, PROF_EPI_WORK, PROF_CTA, PROF_TILES };
+//   8 pipelined launches: producer warp 0 waiting for the neighbouring roles (dataflow + back-pressure)
+enum { PROF_PROD_WAIT = 0, PROF_MMA_WAIT_FULL, PROF_MMA_WAIT_ACC, PROF_MMA_ISSUE, PROF_EPI_WAIT, PROF_EPI_WORK, PROF_CTA, PROF_TILES, PROF_SYNC_WAIT };
 
 struct GemmSmem {
     uint32_t w_off, jobs_off, stage_off, stage_bytes, param_off, bar_off, total;
@@ -68,7 +71,7 @@ __host__ __device__ inline GemmSmem gemm_smem_layout(int cin, int cout, int n_wt
     // shift[cout] (mode 0) / channel sums [2][..] + BatchNorm coefficients xa, xb, ya, yb [4][..] (mode 1)
     s.bar_off = s.param_off + 6u * static_cast<uint32_t>((cout + 31) / 32 * 32) * sizeof(float);
     s.bar_off = (s.bar_off + 15u) & ~15u;
-    s.total = s.bar_off + (2 * kMaxStages + 2 * kAccStages + 1 + kIssuers) * 8 + 16;
+    s.total = s.bar_off + (2 * kMaxStages + 2 * kAccStages + 1 + kIssuers) * 8 + 48;   // + TMEM slot, arrival counter, watermarks
     return s;
 }
 
@@ -91,10 +94,14 @@ struct TileWalk {
 //                      sum / sum of squares of the fp32 accumulators over the real pixels (BatchNorm batch statistics).
 // DUAL: the CTA allocates 256 instead of 512 accumulator columns and half of the shared memory, so that two CTAs share an SM
 // (narrow inference layers, whose small MMAs leave the tensor pipe, the copy engine and the epilogue warps idle in turn).
-template <int CIN, int COUT, int MODE, bool DUAL = false>
-__global__ void __launch_bounds__(kGemmThreads, DUAL ? 2 : 1)
-gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
+// SYNC: the CTA is one of `n_cta` CTAs of role `role` of a layer-pipelined launch P (ld_types.h, GemmMultiParams): its producer
+// warps wait for the m-tiles of the upstream roles a tile reads (and for its consumer not to fall more than lead_max m-tiles
+// behind), its epilogue warps signal every finished tile.  Otherwise `cta` / `n_cta` are blockIdx.x / gridDim.x and P is unused.
+template <int CIN, int COUT, int MODE, bool DUAL, bool SYNC>
+__device__ __forceinline__ void gemm_taps_body(const GemmParams& L, const int m_tiles, const int M, const int cta, const int n_cta,
+                                               const GemmMultiParams* P, const int role) {
     constexpr int kTmemCols = DUAL ? 256 : ld::kTmemCols;
+    constexpr int kThreads = SYNC ? kPipeThreads : kGemmThreads;
     extern __shared__ __align__(128) uint8_t smem[];
     // the warp index through a shuffle: the compiler then knows it is warp-uniform, and everything the issuing thread derives
     // from it and from the kernel parameters stays on the uniform datapath
@@ -114,6 +121,10 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
     float* s_shift = reinterpret_cast<float*>(smem + lay.param_off);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kAccStages + 1 + kIssuers);
+    uint32_t* sig_cnt = tmem_slot + 1;   // pipelined launches: epilogue-warp arrivals (8 per finished tile), read by the signalling warp
+    uint32_t* prod_done = tmem_slot + 2;   // ... producer warps that have issued their last load
+    int32_t* s_wm = reinterpret_cast<int32_t*>(tmem_slot + 4);   // ... [4] watermarks kept by the polling warp: every m-tile up to s_wm[k] of the
+                                                                 // role 1, 2, 3 places upstream (k = 0..2) / of the consumer (k = 3) is complete
 
     const uint32_t bar_full = smem_u32(bars);                       // [n_stages]
     const uint32_t bar_empty = smem_u32(bars + kMaxStages);         // [n_stages]
@@ -126,9 +137,9 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
     constexpr int kStatAll = (COUT + 31) / 32 * 32;     // smem slots per statistic
     constexpr int kStatN = (COUT / 2 + 31) / 32 * 32;   // channels one epilogue warp reduces at a time (padded to the butterfly width)
     if constexpr (MODE == 0) {
-        for (int i = threadIdx.x; i < COUT; i += kGemmThreads) s_shift[i] = L.shift[i];
+        for (int i = threadIdx.x; i < COUT; i += kThreads) s_shift[i] = L.shift[i];
     } else {
-        for (int i = threadIdx.x; i < 2 * kStatAll; i += kGemmThreads) s_shift[i] = 0.f;
+        for (int i = threadIdx.x; i < 2 * kStatAll; i += kThreads) s_shift[i] = 0.f;
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < n_stages; ++i) {
@@ -140,6 +151,9 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
             mbar_init(bar_acc_empty + 8 * i, kEpiWarps);
         }
         mbar_init(bar_w, 1);
+        *sig_cnt = 0u;
+        *prod_done = 0u;
+        s_wm[0] = s_wm[1] = s_wm[2] = s_wm[3] = -1;
         for (int i = 0; i < kIssuers; ++i) mbar_init(bar_turn + 8 * i, 1);
         mbar_fence_init();
     }
@@ -151,7 +165,7 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (warp >= kProducers + kIssuers) {   // accumulators start at zero: every MMA accumulates (see the epilogue)
+    if (warp >= kProducers + kIssuers && warp < kProducers + kIssuers + kEpiWarps) {   // accumulators start at zero: every MMA accumulates (see the epilogue)
         tmem_zero_cols<kTmemCols>(tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16));
         tmem_wait_st();
     }
@@ -161,7 +175,7 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
 
     const int n_jobs = L.n_jobs;
     const int total_tiles = m_tiles * n_jobs;
-    const int my_tiles = (total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int my_tiles = (total_tiles - cta + n_cta - 1) / n_cta;
     const uint32_t w_addr = smem_u32(smem + lay.w_off);
     const uint32_t stage_addr0 = smem_u32(smem + lay.stage_off);
     const uint32_t box_bytes = static_cast<uint32_t>(ext_alloc) * 16u * kChunks;  // one group's operand block
@@ -209,8 +223,8 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
         const int ring0 = warp * ring_n;
         int stage = 0;       // position inside this producer's ring
         uint32_t phase = 0;
-        long long c_wait = 0;
-        TileWalk tw(blockIdx.x + warp * gridDim.x, n_rings * gridDim.x, n_jobs);
+        long long c_wait = 0, c_sync = 0, c_sync_up = 0;
+        TileWalk tw(cta + warp * n_cta, n_rings * n_cta, n_jobs);
         // L2 prefetch: the ring holds about half a tile of operands, less than the DRAM latency under load covers; the operands
         // of this producer's tile `l2pf` steps ahead are requested into L2 now, so that their ring loads find them there
         const int l2pf = L.l2_prefetch;
@@ -220,6 +234,26 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
             const GemmJob& job = s_jobs[tw.job];
             const int p0 = tw.mt * kTileM;
             const int n_groups = job.n_groups;
+            if constexpr (SYNC) {
+                // dataflow: the polling warp keeps the neighbours' completion watermarks in shared memory; a tile's loads start once
+                // the upstream m-tiles it reads are complete and the consumer is at most lead_max m-tiles behind
+                const long long t0 = profiling ? clock64() : 0;
+                bool waited = false;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int dep = job.dep_back[k];
+                    if (dep != kNoDep && role - 1 - k >= 0 && p0 + dep >= 0 && !(P->sync.dbg & 1)) {
+                        const int need = min(m_tiles - 1, (p0 + dep) / kTileM);
+                        while (static_cast<int>(ld_acquire_cta_shared(smem_u32(s_wm + k))) < need) { __nanosleep(20); }
+                        waited = true;
+                    }
+                }
+                if (waited) fence_proxy_async();   // the acquired (generic-proxy) writes are ordered before this thread's bulk-copy reads
+                const long long t1 = profiling ? clock64() : 0;
+                if (role + 1 < P->n_roles && tw.mt - P->sync.lead_max >= 0 && !(P->sync.dbg & 2))
+                    while (static_cast<int>(ld_acquire_cta_shared(smem_u32(s_wm + 3))) < tw.mt - P->sync.lead_max) { __nanosleep(20); }
+                if (profiling) { const long long t2 = clock64(); c_sync += t2 - t0; c_sync_up += t1 - t0; }
+            }
             if (l2pf > 0) {
                 if (it + l2pf * n_rings < my_tiles) {
                     const GemmJob& pj = s_jobs[tw_pf.job];
@@ -253,7 +287,17 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
                 if (++stage == ring_n) { stage = 0; phase ^= 1; }
             }
         }
-        if (profiling && lane == 0 && warp == 0) atomicAdd(prof + PROF_PROD_WAIT, static_cast<unsigned long long>(c_wait));
+        if constexpr (SYNC) {
+            __syncwarp();
+            if (lane == 0) atomicAdd(prod_done, 1u);
+        }
+        if (profiling && lane == 0 && warp == 0) {
+            atomicAdd(prof + PROF_PROD_WAIT, static_cast<unsigned long long>(c_wait));
+            if (SYNC) {
+                atomicAdd(prof + PROF_SYNC_WAIT, static_cast<unsigned long long>(c_sync));
+                atomicAdd(prof + PROF_SYNC_WAIT + 1, static_cast<unsigned long long>(c_sync_up));
+            }
+        }
     } else if (warp < kProducers + kIssuers) {
         // ------------------------------------------------------------------ MMA issuers (uniform control flow per warp)
         const int iw = warp - kProducers;  // this warp issues tiles iw, iw + n_issuers, ... of the CTA into accumulator stage iw
@@ -289,7 +333,7 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
             // of a ring take turns -- one starts waiting for operands only after the other has seen its last stage
             uint32_t turn_phase = 0;
             const uint32_t d_tmem = tmem_base + acc * (kTmemCols / n_issuers);
-            TileWalk tw(blockIdx.x + ring * gridDim.x, n_rings * gridDim.x, n_jobs);
+            TileWalk tw(cta + ring * n_cta, n_rings * n_cta, n_jobs);
             for (int it = ring, k = 0; it < my_tiles; it += n_rings, ++k, tw.next()) {
                 const GemmJobTaps jt = L.job_taps[tw.job];
                 if ((k % ipr) != slot) {
@@ -342,7 +386,7 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp < kProducers + kIssuers + kEpiWarps) {
         // ------------------------------------------------------------------ epilogue
         const int q = warp & 3;  // TMEM lane quadrant this warp may read
         const int half = (warp - kProducers - kIssuers) >> 2;   // which half of the channels of every output
@@ -385,7 +429,26 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
             }
             __syncwarp();
         }
-        TileWalk tw(blockIdx.x, gridDim.x, n_jobs);
+        TileWalk tw(cta, n_cta, n_jobs);
+        // Completion of a tile (pipelined launches): this warp's share of it has been stored -- one of kEpiWarpsPerTile arrivals on
+        // the CTA's shared-memory counter.  The signalling warp turns eight of them into the device-wide signal: a gpu-scope
+        // fence right behind the stores would stall every epilogue warp for a trip through the saturated memory system per tile.
+        auto signal_done = [&]() {
+            if constexpr (SYNC) {
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    atomicAdd(sig_cnt, 1u);
+                }
+            }
+        };
+        if constexpr (SYNC) {   // the other counter buffer belongs to the previous pipelined launch, complete by now: clear it for the next
+            unsigned* zn = P->sync.done_next;
+            const int n_cnt = P->n_roles * P->sync.m_cap;
+            for (int i = static_cast<int>(blockIdx.x) * (kEpiWarps * 32) + (static_cast<int>(threadIdx.x) - 32 * (kProducers + kIssuers)); i < n_cnt;
+                 i += static_cast<int>(gridDim.x) * (kEpiWarps * 32))
+                zn[i] = 0u;
+        }
         for (int it = 0; it < my_tiles; ++it) {
             const GemmJob& job = s_jobs[tw.job];
             const int p = tw.mt * kTileM + q * 32 + lane;
@@ -543,6 +606,7 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
                 }
             }
             if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
+            if constexpr (SYNC) signal_done();
             if (profiling) c_work += clock64() - t0;
         }
         if (profiling && q == 0 && half == 0 && lane == 0) {
@@ -552,14 +616,84 @@ gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
         }
     }
 
+    else if (warp == kProducers + kIssuers + kEpiWarps + 1) {
+        // ------------------------------------------------------------------ polling warp (pipelined launches only)
+        // Follows the completion counters of up to three upstream roles and of the consumer, 32 m-tiles per read, and publishes
+        // "every m-tile up to here is complete" in shared memory: the producer warps then test a tile's dependencies with one
+        // shared-memory read instead of a round trip to L2 per tile and neighbour.
+        if constexpr (SYNC) {
+            const int m_cap = P->sync.m_cap;
+            int mark[4] = {-1, -1, -1, -1};
+            while (ld_acquire_cta_shared(smem_u32(prod_done)) < static_cast<uint32_t>(kProducers)) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int other = k < 3 ? role - 1 - k : role + 1;
+                    if (other < 0 || other >= P->n_roles || mark[k] >= m_tiles - 1) continue;
+                    const int idx = mark[k] + 1 + lane;
+                    const bool done_l = idx < m_tiles && ld_acquire_gpu(P->sync.done + other * m_cap + idx) >= P->expect[other];
+                    const unsigned ok = __ballot_sync(0xffffffffu, done_l);
+                    const int n = ok == 0xffffffffu ? 32 : __ffs(~ok) - 1;
+                    if (n > 0) {
+                        mark[k] += n;
+                        if (lane == 0) st_release_cta_shared(smem_u32(s_wm + k), static_cast<uint32_t>(mark[k]));
+                    }
+                }
+                __nanosleep(200);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ signalling warp (pipelined launches only)
+        if constexpr (SYNC) {
+            if (lane == 0) {
+                TileWalk tw(cta, n_cta, n_jobs);
+                unsigned* done = P->sync.done + role * P->sync.m_cap;
+                for (int it = 0; it < my_tiles;) {
+                    unsigned c;
+                    while ((c = ld_acquire_cta_shared(smem_u32(sig_cnt))) < static_cast<uint32_t>(kEpiWarps * (it + 1))) __nanosleep(32);
+                    // the eight warps' stores of every tile counted so far were ordered before their arrivals (cta scope); ONE fence
+                    // makes them visible device-wide before the m-tiles' counters move (it costs about a tile's time under load:
+                    // whatever finished meanwhile is signalled with the next one)
+                    const int ready = min(my_tiles, static_cast<int>(c / kEpiWarps));
+                    if (!(P->sync.dbg & 4)) __threadfence();
+                    for (; it < ready; ++it, tw.next()) atomicAdd(done + tw.mt, static_cast<unsigned>(kEpiWarps));
+                }
+            }
+        }
+    }
+
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (warp == kProducers) tmem_dealloc(tmem_base, kTmemCols);
     if (MODE == 1 && L.stats != nullptr)   // (the __syncthreads above ordered the shared-memory atomics)
-        for (int i = threadIdx.x; i < 2 * COUT; i += kGemmThreads)
+        for (int i = threadIdx.x; i < 2 * COUT; i += kThreads)
             atomicAdd(L.stats + i, s_shift[(i < COUT ? 0 : kStatAll) + (i < COUT ? i : i - COUT)]);
-    if (profiling && threadIdx.x == 0) atomicAdd(prof + PROF_CTA, static_cast<unsigned long long>(clock64() - t_cta0));
+    if (profiling && threadIdx.x == 0) {
+        const unsigned long long life = static_cast<unsigned long long>(clock64() - t_cta0);
+        atomicAdd(prof + PROF_CTA, life);
+        // shortest / longest lifetime per tile of a CTA (x 1024): the spread between the CTAs of a launch
+        const unsigned long long per_tile = my_tiles > 0 ? (life << 10) / static_cast<unsigned long long>(my_tiles) : 0ull;
+        if (my_tiles > 0) {
+            atomicMax(prof + PROF_SYNC_WAIT + 2, per_tile);
+            atomicMax(prof + PROF_SYNC_WAIT + 3, ~0ull - per_tile);   // (the minimum, stored inverted: the buffer is cleared with zeros)
+        }
+    }
+}
+
+template <int CIN, int COUT, int MODE, bool DUAL = false>
+__global__ void __launch_bounds__(kGemmThreads, DUAL ? 2 : 1)
+gemm_taps_kernel(const __grid_constant__ GemmParams L, int m_tiles, int M) {
+    gemm_taps_body<CIN, COUT, MODE, DUAL, false>(L, m_tiles, M, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), nullptr, 0);
+}
+
+// Layer-pipelined launch (inference): the CTA looks its role up by block index and runs that layer's program.
+template <int CIN, int COUT, bool DUAL>
+__global__ void __launch_bounds__(kPipeThreads, DUAL ? 2 : 1)
+gemm_taps_pipe_kernel(const __grid_constant__ GemmMultiParams P, int m_tiles, int M) {
+    int role = 0;
+    while (role + 1 < P.n_roles && static_cast<int>(blockIdx.x) >= P.cta0[role + 1]) ++role;
+    gemm_taps_body<CIN, COUT, 0, DUAL, true>(P.role[role], m_tiles, M, static_cast<int>(blockIdx.x) - P.cta0[role], P.cta0[role + 1] - P.cta0[role],
+                                             &P, role);
 }
 
 // Host launcher.
@@ -620,6 +754,70 @@ cudaError_t launch_gemm_taps(GemmLaunch& h, int m_tiles, int M, int num_sms, cud
     LD_GEMM_TRAIN(64, 64); LD_GEMM_TRAIN(64, 32); LD_GEMM_TRAIN(32, 64); LD_GEMM_TRAIN(32, 32);
     LD_GEMM_TRAIN(32, 16); LD_GEMM_TRAIN(16, 32); LD_GEMM_TRAIN(16, 16);
 #undef LD_GEMM_TRAIN
+    return cudaErrorInvalidValue;
+}
+
+// Layer-pipelined launch: `roles[r]` are built launches of one shape (cin, cout, inference, same accumulator budget), `ctas[r]`
+// the CTAs each gets (their sum is the grid).
+template <int CIN, int COUT, bool DUAL>
+static cudaError_t launch_pipe_typed(const GemmMultiParams& P, int grid, int m_tiles, int M, unsigned smem_bytes, cudaStream_t stream) {
+    static PerDeviceOnce attr_set;
+    if (!attr_set.flag()) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_taps_pipe_kernel<CIN, COUT, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(gemm_smem_cap(DUAL ? 256 : ld::kTmemCols)));
+        if (e != cudaSuccess) return e;
+        attr_set.flag() = true;
+    }
+    static const bool pdl = []() { const char* v = std::getenv("LD_GEMM_PDL"); return v == nullptr || std::atoi(v) != 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kPipeThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, gemm_taps_pipe_kernel<CIN, COUT, DUAL>, P, m_tiles, M);
+}
+
+cudaError_t launch_gemm_pipe(GemmLaunch* const* roles, int n_roles, const int* ctas, const GemmSync& sync, int m_tiles, int M,
+                             cudaStream_t stream) {
+    if (n_roles < 1 || n_roles > kMaxRoles || m_tiles > sync.m_cap) return cudaErrorInvalidValue;
+    static thread_local GemmMultiParams P;   // 26 KB: assembled per launch, passed by value
+    unsigned smem = 0;
+    int grid = 0;
+    for (int r = 0; r < n_roles; ++r) {
+        GemmLaunch& h = *roles[r];
+        if (h.mode != 0 || h.cin != roles[0]->cin || h.cout != roles[0]->cout || h.tmem_cols != roles[0]->tmem_cols) return cudaErrorInvalidValue;
+        if (h.jobs_dev == nullptr) {
+            GemmJob* dev = nullptr;
+            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dev), static_cast<size_t>(h.n_jobs) * sizeof(GemmJob));
+            if (e != cudaSuccess) return e;
+            e = cudaMemcpy(dev, h.jobs, static_cast<size_t>(h.n_jobs) * sizeof(GemmJob), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaFree(dev); return e; }
+            h.jobs_dev = dev;
+        }
+        P.role[r] = static_cast<const GemmParams&>(h);
+        P.cta0[r] = grid;
+        grid += ctas[r];
+        P.expect[r] = static_cast<uint32_t>(kEpiWarpsPerTile * h.n_jobs);
+        const GemmSmem lay = gemm_smem_layout(h.cin, h.cout, h.n_wtaps, h.n_jobs, h.ext_alloc, h.groups_per_stage, h.n_stages);
+        smem = lay.total > smem ? lay.total : smem;
+    }
+    for (int r = n_roles; r <= kMaxRoles; ++r) P.cta0[r] = grid;
+    P.n_roles = n_roles;
+    P.sync = sync;
+    const GemmLaunch& h0 = *roles[0];
+    const bool dual = h0.tmem_cols == 256;
+#define LD_PIPE_CASE(ci, co)                                                                                              \
+    if (h0.cin == ci && h0.cout == co) {                                                                                  \
+        if (co <= 32 && dual) return launch_pipe_typed<ci, co, (co <= 32)>(P, grid, m_tiles, M, smem, stream);             \
+        return launch_pipe_typed<ci, co, false>(P, grid, m_tiles, M, smem, stream);                                       \
+    }
+    LD_PIPE_CASE(64, 64); LD_PIPE_CASE(32, 32); LD_PIPE_CASE(16, 16); LD_PIPE_CASE(64, 32); LD_PIPE_CASE(32, 16);
+#undef LD_PIPE_CASE
     return cudaErrorInvalidValue;
 }
 

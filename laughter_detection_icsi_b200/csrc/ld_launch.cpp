@@ -136,6 +136,7 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
     for (size_t j = 0; j < parts.size(); ++j) {
         GemmJob& job = L.jobs[j];
         std::memset(&job, 0, sizeof(job));
+        job.dep_back[0] = job.dep_back[1] = job.dep_back[2] = kNoDep;
         std::vector<Tap>& taps = job_taps[j];
         for (int o = parts[j].first; o < parts[j].second; ++o) {
             if (outs[o].taps.empty()) { err = "output without taps"; return false; }

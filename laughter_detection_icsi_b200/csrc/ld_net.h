@@ -58,6 +58,9 @@ cudaError_t launch_head(const HeadLaunch& L, const ChannelTable& ct, float* prob
 // ld_gemm.cu
 cudaError_t launch_gemm_taps(GemmLaunch& h, int m_tiles, int M, int num_sms, cudaStream_t stream);
 void gemm_release(GemmLaunch& h);   // frees the device copy of the job table
+// layer-pipelined launch of consecutive conv layers of one shape (ld_types.h, GemmMultiParams); ctas[r] = CTAs of role r
+cudaError_t launch_gemm_pipe(GemmLaunch* const* roles, int n_roles, const int* ctas, const GemmSync& sync, int m_tiles, int M,
+                             cudaStream_t stream);
 int gemm_pick_stages(int cin, int cout, int n_wtaps, int n_jobs, int ext_alloc, int groups_per_stage, int max_stages,
                      unsigned smem_cap = 227u * 1024u);
 

@@ -118,6 +118,22 @@ __device__ __forceinline__ void umma_f16_ss_pred(uint32_t d_tmem, uint64_t a_des
 // (launch_dependents), and must not touch memory other kernels produce or consume before wait() returns.
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Dataflow between CTAs of one launch (layer-pipelined conv launches): an acquire load of a completion counter, and the proxy
+// fence that orders the writes it made visible (generic proxy) before this thread's following bulk copies (async proxy).
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_cta_shared(uint32_t addr) {
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(uint32_t addr, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 __device__ __forceinline__ void umma_commit_pred(uint32_t bar, bool issue) {
     asm volatile(

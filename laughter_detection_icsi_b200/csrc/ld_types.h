@@ -78,8 +78,12 @@ struct alignas(16) GemmJob {          // what the producers and the epilogue nee
     GemmOut outs[kMaxOuts];
     int32_t n_groups, n_taps, n_outs, n_stages;  // n_stages = ceil(n_groups / groups_per_stage)
     int64_t out_kc_stride;
-    int64_t pad_;
+    int32_t dep_back[3];   // pipelined launches: last pixel (relative to the tile's first) this job reads of a plane written by the
+                           // role 1, 2, 3 places before its own in the same launch, or kNoDep: the tile's loads wait until the
+                           // m-tiles of that role up to that pixel are complete
+    int32_t pad_;
 };
+constexpr int32_t kNoDep = INT32_MIN;
 // Position of weight row ky inside a stacked block.
 __host__ __device__ inline int w_stack_row(int order, int ky) { return order == 2 ? (ky == 2 ? 0 : ky + 1) : 2 - ky; }
 
@@ -135,6 +139,30 @@ struct GemmParams {         // the kernel's __grid_constant__ parameter
     GemmBwdStats bwd;
     unsigned long long* prof;  // optional: 8 cycle counters per launch (see ld_gemm.cu), null = off
 };
+// ---- layer-pipelined launches ----
+// Consecutive conv layers of one shape (cin, cout) and one resolution run as ROLES of a single launch: role r owns the CTAs
+// [cta0[r], cta0[r + 1]) with its own weights, job table and tap programs, walks its m-tiles in increasing order and signals
+// every finished (job, m-tile) in done[r][m]; the producer warps of role r + 1 load a tile only once the m-tiles of role r it
+// reads are complete.  The layer's output is then consumed out of L2 a few dozen m-tiles after it was written instead of
+// making a round trip through HBM between two launches.
+constexpr int kMaxRoles = 4;
+constexpr int kEpiWarpsPerTile = 8;   // arrivals per finished tile (one per epilogue warp)
+struct GemmSync {
+    unsigned* done;       // [n_roles][m_cap] arrivals per m-tile of this launch; all zero when the launch starts
+    unsigned* done_next;  // the other buffer (previous pipelined launch's counters): zeroed by this launch for the next one
+    int32_t m_cap;        // counters per role
+    int32_t lead_max;     // a role runs at most this many m-tiles ahead of its consumer (keeps the hand-over inside L2)
+    int32_t dbg;          // timing experiments only (LD_GEMM_PIPE_DBG with LD_GEMM_PROF, results are garbage): bit 0 no dataflow waits,
+                          // bit 1 no back-pressure waits, bit 2 no fence before the completion signal
+};
+struct GemmMultiParams {    // the pipelined kernel's __grid_constant__ parameter
+    GemmParams role[kMaxRoles];
+    GemmSync sync;
+    int32_t n_roles;
+    int32_t cta0[kMaxRoles + 1];
+    uint32_t expect[kMaxRoles];   // arrivals that complete an m-tile of role r: kEpiWarpsPerTile * its job count
+};
+
 struct GemmLaunch : GemmParams {   // host side: the parameters plus the job table gemm_build_launch fills;
     GemmJob jobs[kMaxJobs];        // launch_gemm_taps uploads it on first use (jobs_dev), gemm_release frees it
     const uint4* job_tapw(int j) const { return taps + job_taps[j].tap0; }

@@ -372,10 +372,30 @@ class Engine:
     def gemm_macs_per_row(self):
         return float(self.lib.ld_plan_gemm_macs_per_row(self._h))
 
+    def conv_pipeline_groups(self):
+        """Per conv launch of the plan: (group id or -1, CTAs of its role) -- which consecutive conv layers run as the roles of one
+        layer-pipelined kernel launch (ld_conv_pipeline_groups)."""
+        grp, ctas = (ctypes.c_int32 * 64)(), (ctypes.c_int32 * 64)()
+        n = self.lib.ld_conv_pipeline_groups(self._h, grp, ctas, 64)
+        if n < 0:
+            check(n)
+        return [(int(grp[i]), int(ctas[i])) for i in range(n)]
+
+    def conv_launch_names(self):
+        """Name of the kernel launch each conv of the plan belongs to: its own name, or the '+'-joined names of its pipelined group."""
+        names = [c["conv"] for c in _native.plan_json(self.cfg)["convs"]]
+        groups = self.conv_pipeline_groups()
+        joined = {}
+        for name, (g, _) in zip(names, groups):
+            if g >= 0:
+                joined[g] = joined.get(g, []) + [name]
+        return [("+".join(joined[g]) if g >= 0 else name) for name, (g, _) in zip(names, groups)]
+
     @property
     def gemm_plane_bytes_per_row(self):
-        """Algorithmic HBM traffic of the conv stack per sequence row (see _native.plan_plane_bytes_per_row)."""
-        return _native.plan_plane_bytes_per_row(self.cfg)
+        """Algorithmic HBM traffic of the conv stack per sequence row (see _native.plan_plane_bytes_per_row): every plane once per
+        kernel launch that touches it, a layer-pipelined group counting as one launch."""
+        return _native.plan_plane_bytes_per_row(self.cfg, groups=[g for g, _ in self.conv_pipeline_groups()])
 
     def timing_enable(self, enable=True):
         check(self.lib.ld_timing_enable(self._h, int(bool(enable))))
@@ -393,8 +413,10 @@ class Engine:
         n = self.lib.ld_timing_read_convs(self._h, ms, 64, int(bool(reset)))
         if n < 0:
             check(n)
-        names = [c["conv"] for c in _native.plan_json(self.cfg)["convs"]]
-        return [(names[i], ms[i]) for i in range(n)]
+        names = self.conv_launch_names()
+        groups = self.conv_pipeline_groups()
+        # a pipelined group is timed as one launch under its first conv
+        return [(names[i], ms[i]) for i in range(n) if groups[i][0] < 0 or i == 0 or groups[i - 1][0] != groups[i][0]]
 
     def gemm_counters(self, reset=True):
         """LD_GEMM_PROF=1 only: [(conv name, [8 cycle counters])], see include/ld_b200.h."""
@@ -404,6 +426,23 @@ class Engine:
             check(n)
         names = [c["conv"] for c in _native.plan_json(self.cfg)["convs"]]
         return [(names[i], [int(buf[i * 8 + k]) for k in range(8)]) for i in range(n)]
+
+    def gemm_sync_wait(self):
+        """LD_GEMM_PROF=1 only: per conv launch, (cycles producer warp 0 waited for the neighbouring roles of its pipelined launch, the
+        share of them spent waiting for upstream tiles -- the rest is back-pressure from the consumer)."""
+        buf = (ctypes.c_uint64 * 64)()
+        n = self.lib.ld_debug_gemm_sync_wait(self._h, buf, 64)
+        if n < 0:
+            check(n)
+        return [((int(buf[i]) & 0xFFFFFFFF) << 10, (int(buf[i]) >> 32) << 10) for i in range(n)]
+
+    def gemm_cta_spread(self):
+        """LD_GEMM_PROF=1 only: per conv launch, (min, max) CTA lifetime per tile in cycles among the CTAs of its launches."""
+        lo, hi = (ctypes.c_double * 64)(), (ctypes.c_double * 64)()
+        n = self.lib.ld_debug_gemm_cta_spread(self._h, lo, hi, 64)
+        if n < 0:
+            check(n)
+        return [(lo[i], hi[i]) for i in range(n)]
 
     @property
     def kernel_launches(self):

@@ -395,6 +395,30 @@ def test_default_chunk_rows_is_the_benchmarked_configuration():
             assert np.abs(got[off[c] + a:off[c] + b] - ref).max() < tol, (c, a, b)
 
 
+def test_layer_pipelined_launches_are_bit_identical(monkeypatch):
+    """LD_GEMM_PIPE=2 (consecutive conv layers of one shape as roles of one launch, tiles handed over through L2 with
+    device-scope completion counters; off by default) computes exactly what the separate launches compute: three ragged
+    channels over two passes of a 16 384-row context, repeated so that a lost dependency would have many chances to show."""
+    from laughter_detection_icsi_b200.engine import Engine, get_engine
+    base = get_engine(0, chunk_rows=2048)
+    monkeypatch.setenv("LD_GEMM_PIPE", "2")
+    piped = Engine(0, chunk_rows=16384)
+    try:
+        groups = piped.conv_pipeline_groups()
+        assert max(g for g, _ in groups) >= 3 and all(c > 0 for g, c in groups if g >= 0)
+        assert all(g < 0 for g, _ in base.conv_pipeline_groups())
+        T = [17011, 903, 9000]
+        feats = torch.randn(sum(T), 44, device="cuda") * 3 - 4
+        for sd in (synth.synthetic_state_dict(), resnet_oracle.random_state_dict(seed=11)):
+            base.load_state_dict(sd); base.weights_owner = None
+            piped.load_state_dict(sd)
+            want = base.infer_windows(feats, T)
+            for _ in range(4):
+                assert torch.equal(piped.infer_windows(feats, T), want)
+    finally:
+        piped.close()
+
+
 def test_inference_dataloader_generator_form(tmp_path):
     """The reference's own loop (segment_laughter.py:90-100): for model_inputs in create_inference_dataloader(path):
     model(model_inputs[:, None].float().to(device)) in batches of 32 -- same probabilities as the fused fast path."""
