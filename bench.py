@@ -360,6 +360,11 @@ def run_b200(args):
         dense_tf = DENSE_FLOP_PER_WINDOW * windows_per_step * args.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None
         exec_tf = 2 * eng.gemm_macs_per_row * windows_per_step * args.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None
         hbm_gbs = bytes_per_row * windows_per_step * args.steps / (gemm_ms * 1e-3) / 1e9 if gemm_ms else None
+        # third floor: shared-memory traffic of the SS-mode MMAs (operand reads) and of the ring (bulk-copy writes), 128 B/clk/SM at
+        # the SM clock sampled during the timed region
+        smem_r, smem_w = _native.plan_gemm_smem_bytes_per_row(eng.cfg)
+        sm_hz = (clocks or {}).get("sm_mhz") and clocks["sm_mhz"] * 1e6
+        smem_bclk = ((smem_r + smem_w) * windows_per_step * args.steps / (gemm_ms * 1e-3) / torch.cuda.get_device_properties(local_rank).multi_processor_count / sm_hz) if (gemm_ms and sm_hz) else None
         prof = {}
         prof_path = os.path.join(ROOT, "profiles", "latest.json")
         if os.path.exists(prof_path):
@@ -410,6 +415,11 @@ def run_b200(args):
                            "note": f"executed = 2 x {eng.gemm_macs_per_row / 1e6:.1f} MMAC per frame after cross-window reuse (identity "
                                    "residual taps not counted); algorithmic = the dense 1.41666 GFLOP forward per frame the reference "
                                    "computes (bit-identical results)"},
+                "smem": {"unit": "B/clk/SM", "peak": 128.0, "achieved": smem_bclk, "frac": smem_bclk / 128.0 if smem_bclk else None,
+                         "operand_read_bytes_per_frame": smem_r, "bulk_copy_write_bytes_per_frame": smem_w,
+                         "note": "shared-memory traffic of the conv launches: A (4 KB) + B (N x 32 B) operand slabs every SS-mode MMA reads, from "
+                                 "the tap programs, plus the bulk-copy writes of the ring, against 128 B/clk/SM at the SM clock sampled under load. "
+                                 "With cout <= 64 this is the HIGHEST of the three floors of the stack (DESIGN.md section 5): the one that binds"},
                 "kernel_ms_per_step": gemm_ms / args.steps, "kernel_launches_per_step": gemm_launches / args.steps,
                 "kernel_share_of_step": gemm_ms / ms_profiled if ms_profiled else None,
                 "per_conv_ms_per_step": {name: round(v / args.steps, 3) for name, v in conv_ms},

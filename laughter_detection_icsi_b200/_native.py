@@ -178,6 +178,28 @@ def gemm_program_json(cfg=None):
     return json.loads(buf.value.decode())
 
 
+def plan_gemm_smem_bytes_per_row(cfg=None):
+    """Shared-memory traffic of the conv launches per sequence row: what the tensor core reads from shared memory for its SS-mode
+    MMAs (a 128 x 16 A slab = 4 KB and an N x 16 B slab per MMA, straight from the tap programs) plus what the bulk copies write
+    into the ring (every load group of every job once per 128-pixel tile).  At 128 B/clk per SM this is the highest of the three
+    floors of the conv stack (HBM planes, tensor pipe, shared-memory operand bandwidth).
+    Returns (operand_read_bytes, bulk_copy_write_bytes) per row."""
+    prog = gemm_program_json(cfg)["convs"]
+    wp = {c["conv"]: c["wp"] for c in plan_json(cfg)["convs"]}
+    reads = writes = 0.0
+    for c in prog:
+        ks = c["cin"] // 16
+        per_tile_r = per_tile_w = 0
+        for j in c["jobs"]:
+            for x, _, _, w in j["taps"]:
+                k = ks // 2 if (x >> 27) & 1 else ks
+                per_tile_r += k * (128 * 32 + ((w >> 17) & 63) * 8 * 32)
+            per_tile_w += len(j["groups"]) * c["ext_alloc"] * c["cin"] * 2
+        reads += per_tile_r * wp[c["conv"]] / 128.0
+        writes += per_tile_w * wp[c["conv"]] / 128.0
+    return reads, writes
+
+
 def i64_array(values):
     arr = (c_int64 * len(values))(*[int(v) for v in values])
     return arr

@@ -167,6 +167,17 @@ def test_split_precision_plan_and_error_budget():
     assert err_split < 2e-3 and err_split < err_fp16
 
 
+def test_shared_memory_traffic_per_row():
+    """The third floor of the conv stack behind bench.py's `roofline.smem`: the SS-mode MMAs of the tap programs read ~2.7 MB of
+    operand slabs per frame from shared memory and the ring takes ~0.8 MB of bulk copies -- 3.5 MB per frame at 128 B/clk/SM is
+    266 ms per 6-channel-hour step at 1.5 GHz, above the HBM (242 ms) and tensor-pipe (177 ms) floors."""
+    r, w = _native.plan_gemm_smem_bytes_per_row()
+    assert 2.5e6 < r < 2.9e6 and 0.7e6 < w < 0.9e6
+    floor_ms = (r + w) * 2.16e6 / 128 / 148 / 1.5e9 * 1e3
+    assert 250 < floor_ms < 280
+    assert floor_ms > _native.plan_plane_bytes_per_row() * 2.16e6 / 6553.3e9 * 1e3
+
+
 def test_plane_traffic_per_row():
     """The algorithmic HBM traffic of the conv stack behind bench.py's roofline: ~733 KB of fp16 planes per frame, i.e. 85 MAC =
     170 FLOP per byte with the 62.4 MMAC the plan executes -- just left of the B200 ridge (~215 FLOP/B)."""
