@@ -321,7 +321,7 @@ int64_t ld_gemm_program_json(const ld_config* cfg, char* buf, int64_t cap) {
                     for (const auto& js : other.jobs) has_res = has_res || js.res_plane >= 0;
             const int kk = cs.ksize * cs.ksize, n_slabs = kk * (cs.split_w ? 2 : 1) + (has_res ? 1 : 0);
             L.cin = cs.cin * (cs.split_in ? 2 : 1); L.cout = cs.cout; L.n_wtaps = n_slabs;
-            L.relu = cs.relu; L.wp = cs.wp; L.out_mode = cs.out_mode; L.wp2 = cs.wp2; L.hp = cs.hp;
+            L.relu = cs.relu; L.wp = cs.wp; L.w_real = cs.w_real; L.out_mode = cs.out_mode; L.wp2 = cs.wp2; L.hp = cs.hp;
             L.w_stack = cs.ksize == 3 ? 1 : 0;
             L.w_blocks = cs.ksize == 3 ? (cs.split_w ? 2 : 1) : 0;
             L.split_out = cs.split_out;
@@ -473,7 +473,7 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         const ConvWeights& w = ctx->weights[cs.conv];
         L.weights = w.w; L.shift = w.shift;
         L.cin = w.cin_eff(); L.cout = cs.cout; L.n_wtaps = w.n_slabs();
-        L.relu = cs.relu; L.wp = cs.wp; L.out_mode = cs.out_mode; L.wp2 = cs.wp2; L.hp = cs.hp;
+        L.relu = cs.relu; L.wp = cs.wp; L.w_real = cs.w_real; L.out_mode = cs.out_mode; L.wp2 = cs.wp2; L.hp = cs.hp;
         L.mode = 0;
         L.w_stack = cs.ksize == 3 ? 1 : 0;
         L.w_blocks = cs.ksize == 3 ? (w.split_w ? 2 : 1) : 0;
@@ -618,6 +618,7 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
     // stem
     ctx->stem.n_jobs = static_cast<int>(plan.stem.size());
     ctx->stem.W = plan.W;
+    ctx->stem.wp = plan.stem_wp;
     if (ctx->stem.n_jobs > ld::kMaxStemJobs) return cleanup_fail(fail(LD_ERR_INVALID, "too many stem jobs"));
     for (int j = 0; j < ctx->stem.n_jobs; ++j) {
         const auto& sj = plan.stem[j];

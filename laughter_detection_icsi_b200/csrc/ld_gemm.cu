@@ -393,6 +393,7 @@ __device__ __forceinline__ void gemm_taps_body(const GemmParams& L, const int m_
         constexpr int CH = COUT / 2;                             // accumulator columns per epilogue warp
         static_assert(CH % 8 == 0, "cout must be a multiple of 16");
         const int wp = L.wp, wp2 = L.wp2, hp = L.hp, relu = L.relu, out_mode = L.out_mode;
+        const int w_real = L.w_real > 0 ? L.w_real : wp - 2;   // (0: the dense training layout with a pad column on either side)
         const bool split_out = MODE == 0 && L.split_out != 0;
         const uint32_t wp_magic = L.wp_magic;
         const int n_acc = L.n_issuers, acc_cols = kTmemCols / n_acc;
@@ -403,7 +404,7 @@ __device__ __forceinline__ void gemm_taps_body(const GemmParams& L, const int m_
         auto locate = [&](int p, int& row, int& col) -> bool {
             row = static_cast<int>(__umulhi(static_cast<uint32_t>(p), wp_magic));
             col = p - row * wp;
-            bool inner = col >= 1 && col <= wp - 2;
+            bool inner = col >= 1 && col <= w_real;
             if (hp > 0) {
                 const int ri = row % hp;
                 inner = inner && ri >= 1 && ri <= hp - 2;

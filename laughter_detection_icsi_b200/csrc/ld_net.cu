@@ -50,7 +50,7 @@ stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_shift[i] = L.shift[i];
     __syncthreads();
 
-    const int wp = L.W + 2;
+    const int wp = L.wp;   // column 0 = the zero pad shared with the row before (ld_types.h); wp = W + 2: also column W + 1
     const long long n_pix = static_cast<long long>(rows_total) * wp;
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -70,7 +70,7 @@ stem_kernel(StemLaunch L, ChannelTable ct, const float* __restrict__ feats, long
         const int rr = live ? static_cast<int>(p / wp) : 0;
         const int pc = live ? static_cast<int>(p - static_cast<long long>(rr) * wp) : 0;
         const int G = row_lo + rr;                       // chunk-relative global row of the centre tap
-        pad[i] = pc == 0 || pc == wp - 1;
+        pad[i] = pc == 0 || pc > L.W;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             long long local = 0;
@@ -240,7 +240,7 @@ cudaError_t launch_stem(const StemLaunch& L, const ChannelTable& ct, const float
     static const int px_env = []() { const char* v = std::getenv("LD_STEM_PX"); return (v && std::atoi(v) == 4) ? 4 : 2; }();
     const bool fixed0 = L.n_jobs == 3 && L.jobs[0].mask == 6 && L.jobs[1].mask == 3 && L.jobs[2].mask == 7;
     const int px = fixed0 ? px_env : 2;
-    const long long threads = (static_cast<long long>(rows_total) * (L.W + 2) + px - 1) / px;   // 32 * px pixels per warp
+    const long long threads = (static_cast<long long>(rows_total) * L.wp + px - 1) / px;   // 32 * px pixels per warp
     const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
     const bool fixed = L.n_jobs == 3 && L.jobs[0].mask == 6 && L.jobs[1].mask == 3 && L.jobs[2].mask == 7;
     if (!fixed) stem_kernel<2, false><<<grid, 256, 0, stream>>>(L, ct, feats, chunk_row0, rows, lo, rows_total);

@@ -35,6 +35,7 @@ struct StemLaunch {
     const float* scale;  // [64]
     const float* shift;  // [64]
     int n_jobs, W;
+    int wp;              // pixels per stored row: W + 1 (one shared pad column) or W + 2
 };
 
 struct HeadRow {

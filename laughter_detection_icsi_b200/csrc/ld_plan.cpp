@@ -42,6 +42,10 @@ int out_size(int n, int stride) { return (n - 1) / stride + 1; }  // k=3,p=1 and
 
 Plan build_stream_plan(const NetConfig& cfg) {
     Plan plan;
+    // pad columns per stored row: 1 = one zero column shared by consecutive rows (default), 2 = one on either side (the round-1
+    // layout, kept for A/B measurements: LD_PLAN_PAD_COLS=2)
+    const char* pad_env = std::getenv("LD_PLAN_PAD_COLS");
+    const int pad_cols = (pad_env && std::atoi(pad_env) == 2) ? 2 : 1;
     plan.H = cfg.H;
     plan.W = cfg.W;
     std::vector<Level> lv;
@@ -49,7 +53,7 @@ Plan build_stream_plan(const NetConfig& cfg) {
 
     auto new_level = [&](int H, int W, int C, int res, const std::string& tag) {
         Level l;
-        l.H = H; l.W = W; l.C = C; l.res = res; l.tag = tag; l.wp = W + 2;
+        l.H = H; l.W = W; l.C = C; l.res = res; l.tag = tag; l.wp = W + pad_cols;   // one shared pad column per row (ld_types.h)
         lv.push_back(l);
         return static_cast<int>(lv.size()) - 1;
     };
@@ -72,7 +76,7 @@ Plan build_stream_plan(const NetConfig& cfg) {
             const int Ho = out_size(x.H, s), Wo = out_size(x.W, s);
             if (s == 2) {
                 lv[cur].colsplit = true;
-                lv[cur].wp = Wo + 2;
+                lv[cur].wp = Wo + pad_cols;
             }
             const bool split = cfg.precision == 1 && b >= 1;   // blocks 2-4 (tools/precision_budget.py: block1 does not need it)
             const int h = new_level(Ho, Wo, out_c, x.res * s, pre + ".h");
@@ -211,7 +215,8 @@ Plan build_stream_plan(const NetConfig& cfg) {
         ConvLaunchSpec L;
         L.conv = op.conv; L.bn = op.bn;
         L.cin = in.C; L.cout = out.C; L.ksize = op.ksize; L.relu = op.relu;
-        L.wp = out.W + 2;  // geometry of the GEMM's pixel index
+        L.wp = out.W + pad_cols;  // geometry of the GEMM's pixel index
+        L.w_real = out.W;
         L.out_mode = out.colsplit ? OUT_COLSPLIT : OUT_PLAIN;
         L.wp2 = out.wp;
         L.hp = 0;
@@ -318,7 +323,7 @@ std::string plan_to_json(const Plan& plan) {
     for (size_t i = 0; i < plan.convs.size(); ++i) {
         const auto& c = plan.convs[i];
         o << (i ? "," : "") << "{\"conv\":\"" << c.conv << "\",\"bn\":\"" << c.bn << "\",\"cin\":" << c.cin
-          << ",\"cout\":" << c.cout << ",\"ksize\":" << c.ksize << ",\"relu\":" << c.relu << ",\"wp\":" << c.wp
+          << ",\"cout\":" << c.cout << ",\"ksize\":" << c.ksize << ",\"relu\":" << c.relu << ",\"wp\":" << c.wp << ",\"w_real\":" << c.w_real
           << ",\"out_mode\":" << c.out_mode << ",\"wp2\":" << c.wp2 << ",\"hp\":" << c.hp << ",\"split_in\":" << c.split_in
           << ",\"split_out\":" << c.split_out << ",\"split_w\":" << c.split_w << ",\"jobs\":[";
         for (size_t j = 0; j < c.jobs.size(); ++j) {

@@ -7,8 +7,10 @@
 //            for every window that contains g far enough from its edges) or a SPECIFIC plane for one
 //            local row j (value of local row j of the window starting at row b, indexed by b) --
 //            rows whose receptive field touches the window's zero padding.
-//   pixel    flattened (row, padded col) index p = row * wp + col, col in [0, wp), cols 0 and wp-1 are
-//            zero padding.  Planes are fp16, channel-chunk planar: [C/8][pixels][8].
+//   pixel    flattened (row, padded col) index p = row * wp + col, col in [0, wp), wp = W + 1: col 0 is zero
+//            padding and serves BOTH as the left pad of its row and as the right pad of the row before
+//            (p + 1 of a row's last column is the next row's col 0), so 1 / (W + 1) instead of 2 / (W + 2) of
+//            the pixels are padding.  Planes are fp16, channel-chunk planar: [C/8][pixels][8].
 #pragma once
 #include <cstdint>
 #include <string>
@@ -116,6 +118,9 @@ struct GemmParams {         // the kernel's __grid_constant__ parameter
     const float* shift;     // [cout] folded BatchNorm shift (+ conv bias)
     int32_t n_jobs, cin, cout, n_wtaps;
     int32_t relu, wp, out_mode, wp2;
+    int32_t w_real;     // real columns of a row: columns 1..w_real hold data, the others are zero padding.  Inference planes share ONE
+                        // pad column between consecutive rows (wp = w_real + 1: pixel p - 1 of a row's first column and pixel
+                        // p + 1 of its last column are the same kind of zero); 0 = the dense training layout (wp - 2)
     int32_t ext_alloc;  // pixels per loaded group (>= every group's extent, multiple of 8)
     int32_t hp;         // >0: rows per image incl. 2 pad rows (dense layout), pad rows forced to zero
     int32_t n_stages;
@@ -191,6 +196,7 @@ struct ConvLaunchSpec {
     std::string conv;  // state_dict prefix of the conv, e.g. "block2.0.conv1"
     std::string bn;    // state_dict prefix of the BatchNorm that follows
     int cin, cout, ksize, relu, wp, out_mode, wp2, hp;
+    int w_real = 0;   // real columns per row (wp - 1: one shared pad column)
     int split_in = 0, split_out = 0, split_w = 0;   // split precision: [hi | lo] input planes / output planes / hi + lo weights
     std::vector<JobSpec> jobs;
 };

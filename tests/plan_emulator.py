@@ -85,7 +85,7 @@ class PlanEmulator:
             wp = c["wp"]
             M = rows * wp
             col = torch.arange(M) % wp
-            inner = (col >= 1) & (col <= wp - 2)
+            inner = (col >= 1) & (col <= c["w_real"])
             for job in c["jobs"]:
                 acc = torch.zeros(M, c["cout"])
                 for plane, shift, wtap in job["taps"]:

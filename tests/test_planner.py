@@ -154,8 +154,8 @@ def test_split_precision_plan_and_error_budget():
     for c in plan["convs"]:
         assert c["split_w"] == c["split_out"] == int(not c["conv"].startswith("block1"))
         assert c["split_in"] == int(c["conv"].startswith(("block3", "block4", "block2.1")) or c["conv"] == "block2.0.conv2")
-    # blocks 2-4 are 12.4 of the 62.4 MMAC: three (two for block2.0's fp16 input) products per tap
-    assert 62.4e6 < plan["macs_per_row"] < 62.4e6 + 2.0 * 12.5e6
+    # blocks 2-4 are 11.8 of the 60.7 MMAC: three (two for block2.0's fp16 input) products per tap
+    assert 60.7e6 < plan["macs_per_row"] < 60.7e6 + 2.0 * 12.0e6
     assert _native.plan_plane_bytes_per_row(cfg) > _native.plan_plane_bytes_per_row() + 200e3
     sd = synth.synthetic_state_dict()
     nb = 48
@@ -168,20 +168,21 @@ def test_split_precision_plan_and_error_budget():
 
 
 def test_shared_memory_traffic_per_row():
-    """The third floor of the conv stack behind bench.py's `roofline.smem`: the SS-mode MMAs of the tap programs read ~2.7 MB of
-    operand slabs per frame from shared memory and the ring takes ~0.8 MB of bulk copies -- 3.5 MB per frame at 128 B/clk/SM is
-    266 ms per 6-channel-hour step at 1.5 GHz, above the HBM (242 ms) and tensor-pipe (177 ms) floors."""
+    """The third floor of the conv stack behind bench.py's `roofline.smem`: the SS-mode MMAs of the tap programs read ~2.6 MB of
+    operand slabs per frame from shared memory and the ring takes ~0.77 MB of bulk copies -- 3.4 MB per frame at 128 B/clk/SM is
+    257 ms per 6-channel-hour step at 1.5 GHz, above the HBM (231 ms) and tensor-pipe (186 ms) floors."""
     r, w = _native.plan_gemm_smem_bytes_per_row()
     assert 2.5e6 < r < 2.9e6 and 0.7e6 < w < 0.9e6
     floor_ms = (r + w) * 2.16e6 / 128 / 148 / 1.5e9 * 1e3
-    assert 250 < floor_ms < 280
+    assert 245 < floor_ms < 270
     assert floor_ms > _native.plan_plane_bytes_per_row() * 2.16e6 / 6553.3e9 * 1e3
 
 
 def test_plane_traffic_per_row():
-    """The algorithmic HBM traffic of the conv stack behind bench.py's roofline: ~733 KB of fp16 planes per frame, i.e. 85 MAC =
-    170 FLOP per byte with the 62.4 MMAC the plan executes -- just left of the B200 ridge (~215 FLOP/B)."""
+    """The algorithmic HBM traffic of the conv stack behind bench.py's roofline: ~702 KB of fp16 planes per frame (rows of W + 1 pixels:
+    one shared zero column), i.e. 86 MAC = 173 FLOP per byte with the 60.7 MMAC the plan executes -- just left of the B200 ridge
+    (~215 FLOP/B)."""
     b = _native.plan_plane_bytes_per_row()
-    assert b == 732928.0
+    assert b == 702080.0
     plan = _native.plan_json()
     assert 80 < 2 * plan["macs_per_row"] / b < 180
