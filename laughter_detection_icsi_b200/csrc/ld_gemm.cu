@@ -407,7 +407,7 @@ __device__ __forceinline__ void gemm_taps_body(const GemmParams& L, const int m_
             bool inner = col >= 1 && col <= w_real;
             if (hp > 0) {
                 const int ri = row % hp;
-                inner = inner && ri >= 1 && ri <= hp - 2;
+                inner = inner && ri >= 1 && ri <= hp - (wp - w_real);   // as many pad rows per image as pad columns per row
             }
             return inner;
         };
