@@ -194,7 +194,7 @@ def plan_gemm_smem_bytes_per_row(cfg=None):
             for x, _, _, w in j["taps"]:
                 k = ks // 2 if (x >> 27) & 1 else ks
                 per_tile_r += k * (128 * 32 + ((w >> 17) & 63) * 8 * 32)
-            per_tile_w += len(j["groups"]) * c["ext_alloc"] * c["cin"] * 2
+            per_tile_w += len(j["groups"]) * c.get("ext_copy", c["ext_alloc"]) * c["cin"] * 2
         reads += per_tile_r * wp[c["conv"]] / 128.0
         writes += per_tile_w * wp[c["conv"]] / 128.0
     return reads, writes

@@ -340,7 +340,7 @@ int64_t ld_gemm_program_json(const ld_config* cfg, char* buf, int64_t cap) {
             if (!ld::gemm_build_launch(L, jobs, tune, err)) { fail(LD_ERR_INVALID, "conv " + cs.conv + ": " + err); return -1; }
             if (li) s += ",";
             s += "{\"conv\":\"" + cs.conv + "\",\"cin\":" + std::to_string(L.cin) + ",\"cout\":" + std::to_string(L.cout) +
-                 ",\"w_stack\":" + std::to_string(L.w_stack) + ",\"w_blocks\":" + std::to_string(L.w_blocks) + ",\"ext_alloc\":" + std::to_string(L.ext_alloc) +
+                 ",\"w_stack\":" + std::to_string(L.w_stack) + ",\"w_blocks\":" + std::to_string(L.w_blocks) + ",\"ext_alloc\":" + std::to_string(L.ext_alloc) + ",\"ext_copy\":" + std::to_string(L.ext_copy) +
                  ",\"groups_per_stage\":" + std::to_string(L.groups_per_stage) + ",\"n_stages\":" + std::to_string(L.n_stages) +
                  ",\"n_rings\":" + std::to_string(L.n_rings) + ",\"n_issuers\":" + std::to_string(L.n_issuers) + ",\"tmem_cols\":" + std::to_string(L.tmem_cols) + ",\"jobs\":[";
             for (int j = 0; j < L.n_jobs; ++j) {

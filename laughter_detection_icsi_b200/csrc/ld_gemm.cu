@@ -214,6 +214,7 @@ __device__ __forceinline__ void gemm_taps_body(const GemmParams& L, const int m_
         if (warp == 0) griddep_wait();   // the previous kernel's planes are complete and visible from here on
         mbar_wait(bar_w, 0);   // the job table (and the weights) are in shared memory
         const uint32_t lbo_a = static_cast<uint32_t>(ext_alloc) * 16u;  // bytes between channel chunks of a group
+        const uint32_t copy_a = static_cast<uint32_t>(L.ext_copy > 0 ? L.ext_copy : ext_alloc) * 16u;   // bytes one bulk copy transfers
         // Two independent pipelines: producer w fills ring w (stages [w * ring_n, (w + 1) * ring_n)) with the tiles
         // it = w, w + 2, ... of the CTA; issuer w drains it.  A ring is filled and drained in tile order, stage by stage,
         // so nobody ever waits more than one phase ahead on its parity-tracked barriers.
@@ -274,7 +275,7 @@ __device__ __forceinline__ void gemm_taps_body(const GemmParams& L, const int m_
                     const long long t0 = profiling ? clock64() : 0;
                     mbar_wait(bar_empty + 8 * (ring0 + stage), phase ^ 1);
                     if (profiling) c_wait += clock64() - t0;
-                    mbar_expect_tx(full, lbo_a * n_copies);
+                    mbar_expect_tx(full, copy_a * n_copies);
                 }
                 __syncwarp();
                 const uint32_t dst0 = stage_addr0 + (ring0 + stage) * lay.stage_bytes;
@@ -282,7 +283,7 @@ __device__ __forceinline__ void gemm_taps_body(const GemmParams& L, const int m_
                     const int g = c / kChunks, kc = c - g * kChunks;
                     const GemmGroup& grp = job.groups[g0 + g];
                     bulk_g2s(dst0 + g * box_bytes + kc * lbo_a, grp.src + static_cast<long long>(p0 + grp.shift) * 8 + kc * grp.kc_stride,
-                             lbo_a, full);
+                             copy_a, full);
                 }
                 if (++stage == ring_n) { stage = 0; phase ^= 1; }
             }

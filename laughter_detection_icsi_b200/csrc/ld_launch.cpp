@@ -178,6 +178,7 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
         max_groups = std::max(max_groups, job.n_groups);
     }
     L.ext_alloc = (ext_max + 7) & ~7;
+    L.ext_copy = ext_max;
     L.wp_magic = static_cast<uint32_t>((1ull << 32) / static_cast<unsigned>(L.wp)) + 1u;
 
     // ---- 3. smem ring: a stage holds consecutive groups of a job up to ~stage_bytes (small-K layers: fewer barrier trips)

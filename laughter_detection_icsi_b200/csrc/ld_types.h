@@ -122,6 +122,8 @@ struct GemmParams {         // the kernel's __grid_constant__ parameter
                         // pad column between consecutive rows (wp = w_real + 1: pixel p - 1 of a row's first column and pixel
                         // p + 1 of its last column are the same kind of zero); 0 = the dense training layout (wp - 2)
     int32_t ext_alloc;  // pixels per loaded group (>= every group's extent, multiple of 8)
+    int32_t ext_copy;   // pixels the bulk copies actually transfer per channel chunk of a group: the largest group extent (the
+                        // MMAs never read the rounding slack of ext_alloc)
     int32_t hp;         // >0: rows per image incl. 2 pad rows (dense layout), pad rows forced to zero
     int32_t n_stages;
     int32_t groups_per_stage;  // consecutive groups of a job that share one smem stage (one barrier round trip)
