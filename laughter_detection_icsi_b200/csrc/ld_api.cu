@@ -605,8 +605,6 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
             if (g.ctas[big] < 1) return cleanup_fail(fail(LD_ERR_INVALID, "pipelined launch: CTA split failed"));
         }
         if (!ctx->pipe_groups.empty()) {
-            int wp_min = 1 << 30;
-            for (const auto& cd : ctx->convs) wp_min = std::min(wp_min, cd.wp);
             ctx->pipe_m_cap = (ctx->rows_alloc * 64 + ld::kTileM - 1) / ld::kTileM + 1;   // wp <= 64
             for (int b = 0; b < 2; ++b) {
                 const size_t bytes = static_cast<size_t>(ld::kMaxRoles) * ctx->pipe_m_cap * sizeof(unsigned);
