@@ -37,8 +37,14 @@ def test_plan_structure():
     assert 55e6 < plan["macs_per_row"] < 70e6
 
 
-def test_emulated_plan_matches_dense_windows():
+@pytest.mark.parametrize("pad_cols", [1, 2])
+def test_emulated_plan_matches_dense_windows(pad_cols, monkeypatch):
+    """Executing the plan's tap lists plane by plane reproduces the dense per-window forward -- with ONE zero column shared by
+    consecutive rows (default: wp = W + 1, pixel p + 1 of a row's last column is the next row's pad) and with the round-1 layout
+    of a zero column on either side (LD_PLAN_PAD_COLS=2, kept for A/B runs)."""
+    monkeypatch.setenv("LD_PLAN_PAD_COLS", str(pad_cols))
     plan = _native.plan_json()
+    assert all(c["wp"] == c["w_real"] + pad_cols for c in plan["convs"]) and plan["stem_wp"] == 44 + pad_cols
     sd = resnet_oracle.random_state_dict(seed=3)
     rng = np.random.default_rng(0)
     T = 117  # includes 99 tail windows that see zero padding
