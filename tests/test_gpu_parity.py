@@ -395,6 +395,7 @@ def test_default_chunk_rows_is_the_benchmarked_configuration():
             assert np.abs(got[off[c] + a:off[c] + b] - ref).max() < tol, (c, a, b)
 
 
+@pytest.mark.timeout(300, method="thread")   # the roles spin on device-scope counters: never let a lost signal hang the box
 def test_layer_pipelined_launches_are_bit_identical(monkeypatch):
     """LD_GEMM_PIPE=2 (consecutive conv layers of one shape as roles of one launch, tiles handed over through L2 with
     device-scope completion counters; off by default) computes exactly what the separate launches compute: three ragged
