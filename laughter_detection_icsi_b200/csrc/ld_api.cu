@@ -48,12 +48,8 @@ struct ConvWeights {
     bool has_res = false;  // the launches of this conv add a residual: one extra identity weight slab
     bool split_in = false, split_w = false;  // split precision: [hi | lo] input channels / hi + lo weight blocks
     int cin_eff() const { return cin * (split_in ? 2 : 1); }
-    int n_slabs() const { return ksize * ksize * (split_w ? 2 : 1) + (has_res ? 1 : 0) + (aux_conv.empty() ? 0 : 1); }
+    int n_slabs() const { return ksize * ksize * (split_w ? 2 : 1) + (has_res ? 1 : 0); }
     std::string conv, bn;
-    // the block's 1x1 shortcut conv merged into this conv's launches (LD_GEMM_MERGE_SC=1): its weights are the last slab, its
-    // outputs extra jobs with their own BatchNorm shift and no ReLU -- they read planes the 3x3 jobs of the same tiles just loaded
-    std::string aux_conv, aux_bn;
-    float* shift_aux = nullptr;
 };
 
 constexpr int kProfSlots = 16;   // cycle counters per conv launch (LD_GEMM_PROF=1; ld_debug_gemm_counters reports the first 8)
@@ -143,7 +139,6 @@ struct ld_ctx {
     std::vector<PlaneDev> planes;
     std::map<std::string, ConvWeights> weights;
     std::vector<ConvLaunchDev> convs;
-    std::vector<int> merged_into;   // per conv launch of the plan: the launch that also computes it (1x1 shortcut merged into conv1), or -1
     ld::StemLaunch stem{};
     ld::HeadLaunch head{};
     float* stem_params = nullptr;  // w[576] scale[64] shift[64]
@@ -443,34 +438,11 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
     }
 
     // ---- weights (allocated now so that launch tables can point at them; filled by load_weights) -----
-    ctx->merged_into.assign(plan.convs.size(), -1);
-    {   // LD_GEMM_MERGE_SC=1: a 1x1 shortcut launch that follows a 3x3 conv launch of the same shape reading the same planes becomes
-        // extra jobs of that launch (plain fp16 only, not together with the layer-pipelined launches)
-        const char* v = std::getenv("LD_GEMM_MERGE_SC");
-        const char* pipe = std::getenv("LD_GEMM_PIPE");
-        if (v && std::atoi(v) != 0 && !(pipe && std::atoi(pipe) != 0))
-            for (size_t li = 0; li + 1 < plan.convs.size(); ++li) {
-                const auto& a = plan.convs[li];
-                const auto& b = plan.convs[li + 1];
-                bool a_res = false;
-                for (const auto& js : a.jobs) a_res = a_res || js.res_plane >= 0;
-                if (a.ksize == 3 && b.ksize == 1 && a.cin == b.cin && a.cout == b.cout && a.wp == b.wp && a.out_mode == ld::OUT_PLAIN &&
-                    b.out_mode == ld::OUT_PLAIN && !a.split_in && !a.split_w && !b.split_in && !b.split_w && !a_res &&
-                    a.jobs.size() + b.jobs.size() <= static_cast<size_t>(ld::kMaxJobs) * 4)
-                    ctx->merged_into[li + 1] = static_cast<int>(li);
-            }
-    }
-    for (size_t wi = 0; wi < plan.convs.size(); ++wi) {
-        const auto& cs = plan.convs[wi];
-        if (ctx->merged_into[wi] >= 0) continue;   // its weights live in the slab table of the launch it is merged into
+    for (const auto& cs : plan.convs) {
         if (ctx->weights.count(cs.conv)) continue;
         ConvWeights w;
         w.cin = cs.cin; w.cout = cs.cout; w.ksize = cs.ksize; w.conv = cs.conv; w.bn = cs.bn;
         w.split_in = cs.split_in != 0; w.split_w = cs.split_w != 0;
-        if (wi + 1 < plan.convs.size() && ctx->merged_into[wi + 1] == static_cast<int>(wi)) {
-            w.aux_conv = plan.convs[wi + 1].conv; w.aux_bn = plan.convs[wi + 1].bn;
-            LD_CUDA_C(cudaMalloc(reinterpret_cast<void**>(&w.shift_aux), cs.cout * sizeof(float)));
-        }
         for (const auto& other : plan.convs)
             if (other.conv == cs.conv)
                 for (const auto& js : other.jobs) w.has_res = w.has_res || js.res_plane >= 0;
@@ -498,8 +470,6 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
         ConvLaunchDev& cd = ctx->convs[li];
         ld::GemmLaunch& L = cd.h;
         std::memset(&L, 0, sizeof(L));
-        cd.wp = cs.wp;
-        if (ctx->merged_into[li] >= 0) continue;   // computed by the launch before it
         const ConvWeights& w = ctx->weights[cs.conv];
         L.weights = w.w; L.shift = w.shift;
         L.cin = w.cin_eff(); L.cout = cs.cout; L.n_wtaps = w.n_slabs();
@@ -531,22 +501,6 @@ int ld_create(int device, const ld_config* cfg_in, ld_ctx** out) {
             jobs[j].out0 = ctx->planes[js.out0].base;
             jobs[j].out1 = js.out1 >= 0 ? ctx->planes[js.out1].base : nullptr;
             jobs[j].out_kc_stride = ctx->planes[js.out0].kc_stride;
-        }
-        if (!w.aux_conv.empty()) {   // the merged 1x1 shortcut: one tap per output against the last weight slab
-            const auto& as = plan.convs[li + 1];
-            L.shift_aux = w.shift_aux; L.relu_aux = as.relu;
-            for (const auto& js : as.jobs) {
-                ld::HostJob hj;
-                for (const auto& t : js.taps) {
-                    const PlaneDev& pd = ctx->planes[t.plane];
-                    if (pd.C != L.cin || pd.wp != cs.wp) return cleanup_fail(fail(LD_ERR_INVALID, "plan/plane mismatch in " + as.conv));
-                    hj.taps.push_back({pd.base, pd.kc_stride, t.shift, w.n_slabs() - 1, 0});
-                }
-                hj.out0 = ctx->planes[js.out0].base;
-                hj.out_kc_stride = ctx->planes[js.out0].kc_stride;
-                hj.aux = 1;
-                jobs.push_back(hj);
-            }
         }
         std::string err;
         if (!ld::gemm_build_launch(L, jobs, tune, err)) return cleanup_fail(fail(LD_ERR_INVALID, "conv " + cs.conv + ": " + err));
@@ -709,7 +663,6 @@ void ld_destroy(ld_ctx* ctx) {
     for (auto& kv : ctx->weights) {
         if (kv.second.w) cudaFree(kv.second.w);
         if (kv.second.shift) cudaFree(kv.second.shift);
-        if (kv.second.shift_aux) cudaFree(kv.second.shift_aux);
     }
     if (ctx->stem_params) cudaFree(ctx->stem_params);
     if (ctx->head_params) cudaFree(ctx->head_params);
@@ -772,21 +725,6 @@ int ld_resnet_load_weights(ld_ctx* ctx, const ld_tensor* t, int32_t n) {
                         if (cw.split_in) packed[tap * slab + static_cast<size_t>(kch) * cw.cout * 8 + at] = hi;
                         if (cw.split_w) packed[(taps + tap) * slab + at] = __float2half_rn(v - __half2float(hi));
                     }
-        if (!cw.aux_conv.empty()) {   // the merged 1x1 shortcut: last slab, scaled by ITS BatchNorm; its shift goes to shift_aux
-            const ld_tensor* aw = find_tensor(t, n, cw.aux_conv + ".weight");
-            const ld_tensor* ab = find_tensor(t, n, cw.aux_conv + ".bias");
-            if (!aw || aw->numel != static_cast<int64_t>(cw.cin) * cw.cout)
-                return fail(LD_ERR_INVALID, "state_dict is missing or mis-sized: " + cw.aux_conv + ".weight");
-            if (ab && ab->numel != cw.cout) return fail(LD_ERR_INVALID, "mis-sized " + cw.aux_conv + ".bias");
-            std::vector<float> scale2, shift2;
-            if (int r = fold_bn(t, n, cw.aux_bn, ab ? ab->data : nullptr, cw.cout, scale2, shift2)) return r;
-            for (int kc = 0; kc < kch; ++kc)
-                for (int o = 0; o < cw.cout; ++o)
-                    for (int e = 0; e < 8; ++e)
-                        packed[static_cast<size_t>(cw.n_slabs() - 1) * slab + (static_cast<size_t>(kc) * cw.cout + o) * 8 + e] =
-                            __float2half_rn(aw->data[static_cast<size_t>(o) * cw.cin + kc * 8 + e] * scale2[o]);
-            LD_CUDA(cudaMemcpy(cw.shift_aux, shift2.data(), cw.cout * sizeof(float), cudaMemcpyHostToDevice));
-        }
         LD_CUDA(cudaMemcpy(cw.w, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
         LD_CUDA(cudaMemcpy(cw.shift, shift.data(), cw.cout * sizeof(float), cudaMemcpyHostToDevice));
     }
@@ -834,7 +772,6 @@ int ld_resnet_infer_windows(ld_ctx* ctx, const float* feats_d, const int64_t* ch
         { Timed t(ctx, stream, 1); LD_CUDA(ld::launch_stem(ctx->stem, ct, feats_d, row0, rows, stream)); }
         for (size_t ci = 0; ci < ctx->convs.size(); ++ci) {
             auto& cd = ctx->convs[ci];
-            if (!ctx->merged_into.empty() && ctx->merged_into[ci] >= 0) continue;   // computed by the launch before it
             const int M = rows * cd.wp;
             const int m_tiles = (M + ld::kTileM - 1) / ld::kTileM;
             const int gi = ctx->conv_group.empty() ? -1 : ctx->conv_group[ci];

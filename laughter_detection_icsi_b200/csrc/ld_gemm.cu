@@ -137,10 +137,7 @@ __device__ __forceinline__ void gemm_taps_body(const GemmParams& L, const int m_
     constexpr int kStatAll = (COUT + 31) / 32 * 32;     // smem slots per statistic
     constexpr int kStatN = (COUT / 2 + 31) / 32 * 32;   // channels one epilogue warp reduces at a time (padded to the butterfly width)
     if constexpr (MODE == 0) {
-        for (int i = threadIdx.x; i < COUT; i += kThreads) {
-            s_shift[i] = L.shift[i];
-            if (L.shift_aux != nullptr) s_shift[kStatAll + i] = L.shift_aux[i];   // (mode 0 uses only the first slot of the region)
-        }
+        for (int i = threadIdx.x; i < COUT; i += kThreads) s_shift[i] = L.shift[i];
     } else {
         for (int i = threadIdx.x; i < 2 * kStatAll; i += kThreads) s_shift[i] = 0.f;
     }
@@ -474,9 +471,6 @@ __device__ __forceinline__ void gemm_taps_body(const GemmParams& L, const int m_
             if (L.dbg & 4) do_store = false;
             const long long out_kc = job.out_kc_stride;
             const int n_outs = job.n_outs;
-            // a merged auxiliary conv (the block's 1x1 shortcut) has its own BatchNorm shift and no ReLU
-            const float* sh_base = (MODE == 0 && job.aux) ? s_shift + kStatAll : s_shift;
-            const int relu_t = (MODE == 0 && job.aux) ? L.relu_aux : relu;
             tw.next();
 
             // backward statistics: this pixel's z (and y) values are fetched while the MMAs of the tile still run
@@ -525,8 +519,8 @@ __device__ __forceinline__ void gemm_taps_body(const GemmParams& L, const int m_
                     if (do_store) {
 #pragma unroll
                         for (int kc = 0; kc < CH / 8; ++kc) {
-                            const float4 sh0 = *reinterpret_cast<const float4*>(sh_base + half * CH + kc * 8);
-                            const float4 sh1 = *reinterpret_cast<const float4*>(sh_base + half * CH + kc * 8 + 4);
+                            const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + half * CH + kc * 8);
+                            const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + half * CH + kc * 8 + 4);
                             const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
                             uint4 ov;
                             __half2* oh = reinterpret_cast<__half2*>(&ov);
@@ -535,7 +529,7 @@ __device__ __forceinline__ void gemm_taps_body(const GemmParams& L, const int m_
                                 const int c = kc * 8 + 2 * e;
                                 float a = __uint_as_float(v[c]) + sh[2 * e];
                                 float b = __uint_as_float(v[c + 1]) + sh[2 * e + 1];
-                                if (relu_t) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                                if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                                 oh[e] = __floats2half2_rn(a, b);
                             }
                             if (!inner) ov = make_uint4(0u, 0u, 0u, 0u);
@@ -548,7 +542,7 @@ __device__ __forceinline__ void gemm_taps_body(const GemmParams& L, const int m_
                                     const int c = kc * 8 + 2 * e;
                                     float a = __uint_as_float(v[c]) + sh[2 * e];
                                     float b = __uint_as_float(v[c + 1]) + sh[2 * e + 1];
-                                    if (relu_t) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                                    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                                     const float2 hi = __half22float2(oh[e]);
                                     lh[e] = __floats2half2_rn(a - hi.x, b - hi.y);
                                 }

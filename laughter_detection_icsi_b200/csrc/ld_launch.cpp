@@ -121,10 +121,7 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
     std::vector<std::pair<int, int>> parts;  // [first, last) output indices
     for (size_t a = 0; a < outs.size();) {
         size_t b = a + 1;
-        // (auxiliary 1x1 outputs pack together like the outputs of a pure 1x1 launch and never join a chain of the main conv)
-        while (max_outs > 1 && b < outs.size() && outs[b].aux == outs[b - 1].aux &&
-               (pack_all || outs[b].aux || shares_input(outs[b - 1], outs[b])))
-            ++b;
+        while (max_outs > 1 && b < outs.size() && (pack_all || shares_input(outs[b - 1], outs[b]))) ++b;
         const int n = static_cast<int>(b - a), n_parts = (n + max_outs - 1) / max_outs;
         for (int i = 0; i < n_parts; ++i)
             parts.push_back({static_cast<int>(a) + i * n / n_parts, static_cast<int>(a) + (i + 1) * n / n_parts});
@@ -148,7 +145,6 @@ static bool build_with(GemmLaunch& L, const std::vector<HostJob>& outs, const Ge
             if (outs[o].out_kc_stride != outs[parts[j].first].out_kc_stride) { err = "outputs of a job differ in layout"; return false; }
         }
         job.n_outs = parts[j].second - parts[j].first;
-        job.aux = outs[parts[j].first].aux;
         job.out_kc_stride = outs[parts[j].first].out_kc_stride;
         std::sort(taps.begin(), taps.end(), [](const Tap& a, const Tap& b) {
             return std::tie(a.src, a.shift, a.out) < std::tie(b.src, b.shift, b.out);

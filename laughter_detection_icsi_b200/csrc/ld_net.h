@@ -79,7 +79,6 @@ struct HostJob {   // one OUTPUT plane; gemm_build_launch packs chains of them i
     void* out0 = nullptr;
     void* out1 = nullptr;
     long long out_kc_stride = 0;
-    int aux = 0;   // output of the auxiliary conv merged into the launch (its own shift, no ReLU; never chained with the main conv's outputs)
 };
 struct GemmTuning {
     int group_span, max_stages, stage_bytes, max_outs, n_rings_max, issuers_wide, issuers_narrow;

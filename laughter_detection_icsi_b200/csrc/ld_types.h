@@ -80,9 +80,6 @@ struct alignas(16) GemmJob {          // what the producers and the epilogue nee
     GemmOut outs[kMaxOuts];
     int32_t n_groups, n_taps, n_outs, n_stages;  // n_stages = ceil(n_groups / groups_per_stage)
     int64_t out_kc_stride;
-    int32_t aux;             // outputs of an auxiliary conv merged into this launch (the 1x1 shortcut next to a block's conv1): the
-                             // epilogue applies GemmParams::shift_aux and relu_aux instead of shift / relu
-    int32_t aux_pad_;
     int32_t dep_back[3];   // pipelined launches: last pixel (relative to the tile's first) this job reads of a plane written by the
                            // role 1, 2, 3 places before its own in the same launch, or kNoDep: the tile's loads wait until the
                            // m-tiles of that role up to that pixel are complete
@@ -119,8 +116,6 @@ struct GemmParams {         // the kernel's __grid_constant__ parameter
                               // epilogue index it per lane; the constant path would thrash on it)
     const __half* weights;  // [n_wtaps][cin/8][cout][8] fp16, BatchNorm scale folded in
     const float* shift;     // [cout] folded BatchNorm shift (+ conv bias)
-    const float* shift_aux; // [cout] the same for the jobs of a merged auxiliary conv (GemmJob::aux), or null
-    int32_t relu_aux, relu_aux_pad_;
     int32_t n_jobs, cin, cout, n_wtaps;
     int32_t relu, wp, out_mode, wp2;
     int32_t w_real;     // real columns of a row: columns 1..w_real hold data, the others are zero padding.  Inference planes share ONE
